@@ -1,0 +1,115 @@
+"""ctypes loader for libfwgpu.so (C ABI declared in include/fwgpu.h).
+
+The library is the product; there is no Python or CPU fallback.  Importing
+this module never needs a GPU (the .so loads and exports its symbols on a
+CPU-only box); every compute entry point fails loudly with FwError when no
+CUDA device is present or the library has not been built.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfwgpu.so")
+
+FW_OK = 0
+FW_ERR_INVALID = -1
+FW_ERR_CUDA = -2
+FW_ERR_DOMAIN = -3
+FW_ERR_NOMEM = -4
+FW_ERR_CAP = -5
+FW_TILE = 128
+
+# every symbol include/fwgpu.h declares (tests check the .so exports them all)
+SYMBOLS = (
+    "fw_version", "fw_last_error", "fw_device_count", "fw_ctx_create", "fw_ctx_destroy",
+    "fw_ctx_set_stream", "fw_ctx_last_launches", "fw_solve", "fw_solve_device", "fw_solve_batched",
+    "fw_solve_batched_device", "fw_ctx_synchronize",
+)
+
+
+class FwError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"fwgpu error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+_lib = None
+
+
+def load():
+    """Load libfwgpu.so; raises FwError if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FwError(FW_ERR_CUDA, f"{LIB_PATH} is missing: run __graft_entry__.build() "
+                                   "(make -C floydwarshall_b200/csrc); there is no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+    L.fw_version.restype = ctypes.c_char_p
+    L.fw_last_error.restype = ctypes.c_char_p
+    L.fw_device_count.restype = ctypes.c_int
+    L.fw_ctx_create.restype = ctypes.c_int
+    L.fw_ctx_create.argtypes = [ctypes.c_int, ctypes.POINTER(vp)]
+    L.fw_ctx_destroy.restype = None
+    L.fw_ctx_destroy.argtypes = [vp]
+    L.fw_ctx_set_stream.restype = ctypes.c_int
+    L.fw_ctx_set_stream.argtypes = [vp, vp]
+    L.fw_ctx_last_launches.restype = i64
+    L.fw_ctx_last_launches.argtypes = [vp]
+    L.fw_ctx_synchronize.restype = ctypes.c_int
+    L.fw_ctx_synchronize.argtypes = [vp]
+    L.fw_solve.restype = ctypes.c_int
+    L.fw_solve.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.fw_solve_device.restype = ctypes.c_int
+    L.fw_solve_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp]
+    L.fw_solve_batched.restype = ctypes.c_int
+    L.fw_solve_batched.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    L.fw_solve_batched_device.restype = ctypes.c_int
+    L.fw_solve_batched_device.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != FW_OK:
+        raise FwError(rc, load().fw_last_error().decode("utf-8", "replace"))
+
+
+class Context:
+    """Owns one fw_ctx (device, stream, workspace)."""
+
+    def __init__(self, device: int = 0):
+        L = load()
+        h = ctypes.c_void_p()
+        check(L.fw_ctx_create(device, ctypes.byref(h)))
+        self._h = h
+        self.device = device
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_stream(self, cuda_stream: int | None):
+        check(load().fw_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        check(load().fw_ctx_synchronize(self._h))
+
+    @property
+    def last_launches(self) -> int:
+        return int(load().fw_ctx_last_launches(self._h))
+
+    def close(self):
+        if self._h:
+            load().fw_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,532 @@
+// libfwgpu.so -- C ABI (include/fwgpu.h) over the sm_100a kernels.
+//
+// Replaces runAlgo (reference src/lib/Algorithms.hs:42-61) behind
+// floydWarshall (Algorithms.hs:19-20).  Host orchestration of the exact-order
+// blocked solve, per k-block of FW_B pivots:
+//   1. fw_tile_kernel      pivot diagonal tile + step-k snapshots
+//   2. fw_colpanel_kernel  pivot column panel  -> Cp / NCp snapshots (N x B)
+//      fw_rowpanel_kernel  pivot row panel     -> Rw snapshots      (B x N)
+//   3. fw_bulk_kernel      everything else against the two snapshot panels
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "../../include/fwgpu.h"
+#include "fw_bulk.cuh"
+#include "fw_common.cuh"
+#include "fw_panel.cuh"
+#include "fw_tile.cuh"
+
+static_assert(FW_B == FW_TILE, "kernel block size and public tile size must agree");
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return (e == cudaErrorMemoryAllocation) ? FW_ERR_NOMEM : FW_ERR_CUDA;
+}
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call);      \
+    } while (0)
+
+// ---------------------------------------------------------------- helper kernels
+// flag bit 0: negative rate; bit 1: rate > 0 (off-diagonal) with next < 0
+__global__ void fw_validate_kernel(const double *rate, const int32_t *next, long long ld, long long stride,
+                                   int n, long long total, int *flag) {
+    int bad = 0;
+    const long long nn = (long long)n * n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long g = e / nn, rem = e - g * nn;
+        const int i = (int)(rem / n), j = (int)(rem - (long long)i * n);
+        if (i == j) continue;  // the diagonal is never read (Algorithms.hs:50,54)
+        const long long off = g * stride + (long long)i * ld + j;
+        const double v = rate[off];
+        if (v < 0.0) bad |= 1;
+        if (v > 0.0 && next[off] < 0) bad |= 2;
+    }
+    if (bad) atomicOr(flag, bad);
+}
+
+// pad region of an npad x npad matrix that holds an n x n problem: NaN / -1
+__global__ void fw_fill_pad_kernel(double *rate, int32_t *next, int32_t *mid, int32_t *csT, int32_t *rs,
+                                   long long ld, int n, int npad) {
+    const long long total = (long long)npad * npad;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / npad), j = (int)(e - (long long)i * npad);
+        if (i < n && j < n) continue;
+        const long long off = (long long)i * ld + j;
+        rate[off] = fw::qnan();
+        next[off] = -1;
+        if (mid) { mid[off] = -1; csT[off] = -1; rs[off] = -1; }
+    }
+}
+
+template <typename T>
+__global__ void fw_copy2d_kernel(T *dst, long long dld, const T *src, long long sld, int rows, int cols) {
+    const long long total = (long long)rows * cols;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / cols), j = (int)(e - (long long)i * cols);
+        dst[(long long)i * dld + j] = src[(long long)i * sld + j];
+    }
+}
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    int ensure(size_t n) {
+        if (n <= cap) return FW_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaMalloc"); }
+        cap = n;
+        return FW_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct fw_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    int64_t launches = 0;
+    // snapshot panels
+    DevBuf<double> Cp, Rw;
+    DevBuf<int32_t> NCp;
+    // padded working copy (n not a multiple of FW_B) and host-API staging
+    DevBuf<double> w_rate;
+    DevBuf<int32_t> w_next, w_mid, w_csT, w_rs;
+    // device staging of the host-buffer batched API
+    DevBuf<double> s_rate;
+    DevBuf<int32_t> s_next, s_mid, s_csT, s_rs;
+    int *d_flag = nullptr;
+    int *h_flag = nullptr;
+    bool attrs_set = false;
+};
+
+namespace {
+
+int set_kernel_attrs(fw_ctx *c) {
+    if (c->attrs_set) return FW_OK;
+    CU(cudaFuncSetAttribute(fw::fw_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::tile_smem_bytes(false)));
+    CU(cudaFuncSetAttribute(fw::fw_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::tile_smem_bytes(true)));
+    CU(cudaFuncSetAttribute(fw::fw_colpanel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::panel_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_colpanel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::panel_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_rowpanel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::panel_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_rowpanel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::panel_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_bulk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    c->attrs_set = true;
+    return FW_OK;
+}
+
+int grid_for(long long total, int sm_count) {
+    long long g = (total + 255) / 256;
+    long long cap = (long long)sm_count * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// Domain check (synchronises the stream once).
+int validate_device(fw_ctx *c, const double *rate, const int32_t *next, long long ld, long long stride,
+                    int batch, int n) {
+    CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+    const long long total = (long long)batch * n * n;
+    fw_validate_kernel<<<grid_for(total, c->sm_count), 256, 0, c->stream>>>(rate, next, ld, stride, n, total,
+                                                                             c->d_flag);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (*c->h_flag & 1) return fail(FW_ERR_DOMAIN, "rate matrix holds a negative entry");
+    if (*c->h_flag & 2) return fail(FW_ERR_DOMAIN, "rate > 0 with next < 0 (inconsistent next-hop matrix)");
+    return FW_OK;
+}
+
+// Blocked solve on a padded (npad % FW_B == 0, pads = NaN) device matrix.
+int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next, int32_t *mid,
+                  int32_t *csT, int32_t *rs) {
+    const bool paths = (mid != nullptr);
+    int rc;
+    if ((rc = c->Cp.ensure((size_t)npad * FW_B)) != FW_OK) return rc;
+    if ((rc = c->NCp.ensure((size_t)npad * FW_B)) != FW_OK) return rc;
+    if ((rc = c->Rw.ensure((size_t)npad * FW_B)) != FW_OK) return rc;
+    const int nblk = npad / FW_B;
+    const int njobs32 = (npad - FW_B) / 32;
+    const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
+    const int nt = npad / fw::BULK_T - FW_B / fw::BULK_T;
+    for (int b = 0; b < nblk; ++b) {
+        const int b0 = b * FW_B;
+        fw::TileArgs t;
+        t.rate = rate; t.next = next; t.mid = mid; t.csT = csT; t.rs = rs;
+        t.ld = ld; t.batch_stride = 0; t.b0 = b0; t.nv = FW_B;
+        t.Cp = c->Cp.p; t.NCp = c->NCp.p; t.Rw = c->Rw.p; t.ldw = npad;
+        if (paths)
+            fw::fw_tile_kernel<true><<<1, 512, fw::tile_smem_bytes(true), c->stream>>>(t);
+        else
+            fw::fw_tile_kernel<false><<<1, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
+        c->launches++;
+        if (nblk > 1) {
+            fw::PanelArgs p;
+            p.rate = rate; p.next = next; p.mid = mid; p.csT = csT; p.rs = rs;
+            p.ld = ld; p.npad = npad; p.b0 = b0;
+            p.Cp = c->Cp.p; p.NCp = c->NCp.p; p.Rw = c->Rw.p; p.ldw = npad;
+            if (paths) {
+                fw::fw_colpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+                fw::fw_rowpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+            } else {
+                fw::fw_colpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+                fw::fw_rowpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+            }
+            c->launches += 2;
+            fw::BulkArgs g;
+            g.rate = rate; g.next = next; g.mid = mid; g.ld = ld; g.npad = npad; g.b0 = b0;
+            g.Cp = c->Cp.p; g.NCp = c->NCp.p; g.Rw = c->Rw.p; g.ldw = npad;
+            fw::fw_bulk_kernel<<<dim3(nt, nt), 128, 0, c->stream>>>(g);
+            c->launches++;
+        }
+        CU(cudaGetLastError());
+    }
+    return FW_OK;
+}
+
+int fill_minus1_2d(fw_ctx *c, int32_t *p, long long ld, int rows, int cols) {
+    CU(cudaMemset2DAsync(p, (size_t)ld * 4, 0xFF, (size_t)cols * 4, (size_t)rows, c->stream));
+    return FW_OK;
+}
+
+// n <= FW_B graphs, one CTA each, directly on the caller's layout.
+int solve_tiles(fw_ctx *c, int batch, int n, long long ld, long long stride, double *rate, int32_t *next,
+                int32_t *mid, int32_t *csT, int32_t *rs) {
+    const bool paths = (mid != nullptr);
+    fw::TileArgs t;
+    t.rate = rate; t.next = next; t.mid = mid; t.csT = csT; t.rs = rs;
+    t.ld = ld; t.batch_stride = stride; t.b0 = 0; t.nv = n;
+    t.Cp = nullptr; t.NCp = nullptr; t.Rw = nullptr; t.ldw = 0;
+    if (paths)
+        fw::fw_tile_kernel<true><<<batch, 512, fw::tile_smem_bytes(true), c->stream>>>(t);
+    else
+        fw::fw_tile_kernel<false><<<batch, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
+    c->launches++;
+    CU(cudaGetLastError());
+    return FW_OK;
+}
+
+int solve_device_locked(fw_ctx *c, int n, long long ld, double *rate, int32_t *next, int32_t *mid,
+                        int32_t *csT, int32_t *rs, bool validate) {
+    int rc;
+    if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
+    if (validate && (rc = validate_device(c, rate, next, ld, 0, 1, n)) != FW_OK) return rc;
+    const bool paths = (mid != nullptr);
+    if (n <= FW_B) {
+        if (paths) {
+            if ((rc = fill_minus1_2d(c, mid, ld, n, n)) != FW_OK) return rc;
+            if ((rc = fill_minus1_2d(c, csT, ld, n, n)) != FW_OK) return rc;
+            if ((rc = fill_minus1_2d(c, rs, ld, n, n)) != FW_OK) return rc;
+        }
+        return solve_tiles(c, 1, n, ld, 0, rate, next, mid, csT, rs);
+    }
+    const bool aligned = (ld % 4 == 0) && !((uintptr_t)rate & 15) && !((uintptr_t)next & 15) &&
+                         (!paths || (!((uintptr_t)mid & 15) && !((uintptr_t)csT & 15) && !((uintptr_t)rs & 15)));
+    if (n % FW_B == 0 && aligned) {
+        if (paths) {
+            if ((rc = fill_minus1_2d(c, mid, ld, n, n)) != FW_OK) return rc;
+            if ((rc = fill_minus1_2d(c, csT, ld, n, n)) != FW_OK) return rc;
+            if ((rc = fill_minus1_2d(c, rs, ld, n, n)) != FW_OK) return rc;
+        }
+        return solve_blocked(c, n, ld, rate, next, mid, csT, rs);
+    }
+    // padded working copy
+    const int npad = (n + FW_B - 1) / FW_B * FW_B;
+    const size_t tot = (size_t)npad * npad;
+    if ((rc = c->w_rate.ensure(tot)) != FW_OK) return rc;
+    if ((rc = c->w_next.ensure(tot)) != FW_OK) return rc;
+    if (paths) {
+        if ((rc = c->w_mid.ensure(tot)) != FW_OK) return rc;
+        if ((rc = c->w_csT.ensure(tot)) != FW_OK) return rc;
+        if ((rc = c->w_rs.ensure(tot)) != FW_OK) return rc;
+        CU(cudaMemsetAsync(c->w_mid.p, 0xFF, tot * 4, c->stream));
+        CU(cudaMemsetAsync(c->w_csT.p, 0xFF, tot * 4, c->stream));
+        CU(cudaMemsetAsync(c->w_rs.p, 0xFF, tot * 4, c->stream));
+    }
+    const int g = grid_for((long long)n * n, c->sm_count);
+    fw_copy2d_kernel<double><<<g, 256, 0, c->stream>>>(c->w_rate.p, npad, rate, ld, n, n);
+    fw_copy2d_kernel<int32_t><<<g, 256, 0, c->stream>>>(c->w_next.p, npad, next, ld, n, n);
+    fw_fill_pad_kernel<<<grid_for((long long)tot, c->sm_count), 256, 0, c->stream>>>(
+        c->w_rate.p, c->w_next.p, nullptr, nullptr, nullptr, npad, n, npad);
+    c->launches += 3;
+    CU(cudaGetLastError());
+    rc = solve_blocked(c, npad, npad, c->w_rate.p, c->w_next.p, paths ? c->w_mid.p : nullptr,
+                       paths ? c->w_csT.p : nullptr, paths ? c->w_rs.p : nullptr);
+    if (rc != FW_OK) return rc;
+    fw_copy2d_kernel<double><<<g, 256, 0, c->stream>>>(rate, ld, c->w_rate.p, npad, n, n);
+    fw_copy2d_kernel<int32_t><<<g, 256, 0, c->stream>>>(next, ld, c->w_next.p, npad, n, n);
+    c->launches += 2;
+    if (paths) {
+        fw_copy2d_kernel<int32_t><<<g, 256, 0, c->stream>>>(mid, ld, c->w_mid.p, npad, n, n);
+        fw_copy2d_kernel<int32_t><<<g, 256, 0, c->stream>>>(csT, ld, c->w_csT.p, npad, n, n);
+        fw_copy2d_kernel<int32_t><<<g, 256, 0, c->stream>>>(rs, ld, c->w_rs.p, npad, n, n);
+        c->launches += 3;
+    }
+    CU(cudaGetLastError());
+    return FW_OK;
+}
+
+fw_ctx *g_default = nullptr;
+std::mutex g_default_mu;
+
+int get_ctx(fw_ctx *in, fw_ctx **out) {
+    if (in) { *out = in; return FW_OK; }
+    std::lock_guard<std::mutex> lk(g_default_mu);
+    if (!g_default) {
+        int rc = fw_ctx_create(0, &g_default);
+        if (rc != FW_OK) return rc;
+    }
+    *out = g_default;
+    return FW_OK;
+}
+
+bool paths_args_ok(const int32_t *mid, const int32_t *csT, const int32_t *rs) {
+    const int k = (mid != nullptr) + (csT != nullptr) + (rs != nullptr);
+    return k == 0 || k == 3;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *fw_version(void) { return "fwgpu 0.1 (sm_100a, exact-order blocked max-times Floyd-Warshall)"; }
+const char *fw_last_error(void) { return g_err.c_str(); }
+
+int fw_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fw_ctx_create(int device, fw_ctx **out) {
+    if (!out || device < 0) return fail(FW_ERR_INVALID, "fw_ctx_create: bad argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(FW_ERR_CUDA, "no CUDA device available (libfwgpu has no CPU fallback)");
+    if (device >= ndev) return fail(FW_ERR_INVALID, "fw_ctx_create: device index out of range");
+    CU(cudaSetDevice(device));
+    fw_ctx *c = new (std::nothrow) fw_ctx();
+    if (!c) return fail(FW_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c; return cuda_fail(e, "cudaStreamCreate");
+    }
+    c->stream = c->own_stream;
+    if ((e = cudaMalloc(&c->d_flag, sizeof(int))) != cudaSuccess) { delete c; return cuda_fail(e, "cudaMalloc"); }
+    if ((e = cudaMallocHost(&c->h_flag, sizeof(int))) != cudaSuccess) { delete c; return cuda_fail(e, "cudaMallocHost"); }
+    *out = c;
+    return FW_OK;
+}
+
+void fw_ctx_destroy(fw_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->Cp.release(); c->Rw.release(); c->NCp.release();
+    c->w_rate.release(); c->w_next.release(); c->w_mid.release(); c->w_csT.release(); c->w_rs.release();
+    c->s_rate.release(); c->s_next.release(); c->s_mid.release(); c->s_csT.release(); c->s_rs.release();
+    if (c->d_flag) cudaFree(c->d_flag);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int fw_ctx_set_stream(fw_ctx *c, void *cuda_stream) {
+    if (!c) return fail(FW_ERR_INVALID, "fw_ctx_set_stream: null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return FW_OK;
+}
+
+int64_t fw_ctx_last_launches(const fw_ctx *c) { return c ? c->launches : 0; }
+
+int fw_ctx_synchronize(fw_ctx *c) {
+    int rc = get_ctx(c, &c);
+    if (rc != FW_OK) return rc;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return FW_OK;
+}
+
+int fw_solve_device(fw_ctx *c, int32_t n, int64_t ld, double *d_rate, int32_t *d_next, int32_t *d_mid,
+                    int32_t *d_csT, int32_t *d_rs) {
+    if (n < 0) return fail(FW_ERR_INVALID, "fw_solve_device: n < 0");
+    if (n == 0) return FW_OK;
+    if (!d_rate || !d_next || ld < n) return fail(FW_ERR_INVALID, "fw_solve_device: bad argument");
+    if (!paths_args_ok(d_mid, d_csT, d_rs)) return fail(FW_ERR_INVALID, "mid/csT/rs: pass all three or none");
+    int rc = get_ctx(c, &c);
+    if (rc != FW_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->launches = 0;
+    return solve_device_locked(c, n, ld, d_rate, d_next, d_mid, d_csT, d_rs, true);
+}
+
+int fw_solve(fw_ctx *c, int32_t n, double *rate, int32_t *next, int32_t *mid, int32_t *csT, int32_t *rs) {
+    if (n < 0) return fail(FW_ERR_INVALID, "fw_solve: n < 0");
+    if (n == 0) return FW_OK;  // floydWarshall M.empty == V.empty
+    if (!rate || !next) return fail(FW_ERR_INVALID, "fw_solve: null buffer");
+    if (!paths_args_ok(mid, csT, rs)) return fail(FW_ERR_INVALID, "mid/csT/rs: pass all three or none");
+    int rc = get_ctx(c, &c);
+    if (rc != FW_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->launches = 0;
+    if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
+    const bool paths = (mid != nullptr);
+    const int npad = (n <= FW_B) ? n : (n + FW_B - 1) / FW_B * FW_B;
+    const size_t tot = (size_t)npad * npad;
+    if ((rc = c->w_rate.ensure(tot)) != FW_OK) return rc;
+    if ((rc = c->w_next.ensure(tot)) != FW_OK) return rc;
+    if (paths) {
+        if ((rc = c->w_mid.ensure(tot)) != FW_OK) return rc;
+        if ((rc = c->w_csT.ensure(tot)) != FW_OK) return rc;
+        if ((rc = c->w_rs.ensure(tot)) != FW_OK) return rc;
+    }
+    CU(cudaMemcpy2DAsync(c->w_rate.p, (size_t)npad * 8, rate, (size_t)n * 8, (size_t)n * 8, n,
+                         cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpy2DAsync(c->w_next.p, (size_t)npad * 4, next, (size_t)n * 4, (size_t)n * 4, n,
+                         cudaMemcpyHostToDevice, c->stream));
+    if ((rc = validate_device(c, c->w_rate.p, c->w_next.p, npad, 0, 1, n)) != FW_OK) return rc;
+    if (paths) {
+        CU(cudaMemsetAsync(c->w_mid.p, 0xFF, tot * 4, c->stream));
+        CU(cudaMemsetAsync(c->w_csT.p, 0xFF, tot * 4, c->stream));
+        CU(cudaMemsetAsync(c->w_rs.p, 0xFF, tot * 4, c->stream));
+    }
+    if (npad != n) {
+        fw_fill_pad_kernel<<<grid_for((long long)tot, c->sm_count), 256, 0, c->stream>>>(
+            c->w_rate.p, c->w_next.p, nullptr, nullptr, nullptr, npad, n, npad);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    if (n <= FW_B)
+        rc = solve_tiles(c, 1, n, npad, 0, c->w_rate.p, c->w_next.p, paths ? c->w_mid.p : nullptr,
+                         paths ? c->w_csT.p : nullptr, paths ? c->w_rs.p : nullptr);
+    else
+        rc = solve_blocked(c, npad, npad, c->w_rate.p, c->w_next.p, paths ? c->w_mid.p : nullptr,
+                           paths ? c->w_csT.p : nullptr, paths ? c->w_rs.p : nullptr);
+    if (rc != FW_OK) return rc;
+    CU(cudaMemcpy2DAsync(rate, (size_t)n * 8, c->w_rate.p, (size_t)npad * 8, (size_t)n * 8, n,
+                         cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpy2DAsync(next, (size_t)n * 4, c->w_next.p, (size_t)npad * 4, (size_t)n * 4, n,
+                         cudaMemcpyDeviceToHost, c->stream));
+    if (paths) {
+        CU(cudaMemcpy2DAsync(mid, (size_t)n * 4, c->w_mid.p, (size_t)npad * 4, (size_t)n * 4, n,
+                             cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpy2DAsync(csT, (size_t)n * 4, c->w_csT.p, (size_t)npad * 4, (size_t)n * 4, n,
+                             cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpy2DAsync(rs, (size_t)n * 4, c->w_rs.p, (size_t)npad * 4, (size_t)n * 4, n,
+                             cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return FW_OK;
+}
+
+int fw_solve_batched_device(fw_ctx *c, int32_t batch, int32_t n, double *d_rate, int32_t *d_next,
+                            int32_t *d_mid, int32_t *d_csT, int32_t *d_rs) {
+    if (n < 0 || batch < 0) return fail(FW_ERR_INVALID, "fw_solve_batched_device: negative size");
+    if (n == 0 || batch == 0) return FW_OK;
+    if (!d_rate || !d_next) return fail(FW_ERR_INVALID, "fw_solve_batched_device: null buffer");
+    if (!paths_args_ok(d_mid, d_csT, d_rs)) return fail(FW_ERR_INVALID, "mid/csT/rs: pass all three or none");
+    int rc = get_ctx(c, &c);
+    if (rc != FW_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->launches = 0;
+    if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
+    const long long stride = (long long)n * n;
+    if ((rc = validate_device(c, d_rate, d_next, n, stride, batch, n)) != FW_OK) return rc;
+    if (n <= FW_B) {
+        if (d_mid) {
+            CU(cudaMemsetAsync(d_mid, 0xFF, (size_t)batch * stride * 4, c->stream));
+            CU(cudaMemsetAsync(d_csT, 0xFF, (size_t)batch * stride * 4, c->stream));
+            CU(cudaMemsetAsync(d_rs, 0xFF, (size_t)batch * stride * 4, c->stream));
+        }
+        return solve_tiles(c, batch, n, n, stride, d_rate, d_next, d_mid, d_csT, d_rs);
+    }
+    for (int g = 0; g < batch; ++g) {
+        const long long o = (long long)g * stride;
+        rc = solve_device_locked(c, n, n, d_rate + o, d_next + o, d_mid ? d_mid + o : nullptr,
+                                 d_csT ? d_csT + o : nullptr, d_rs ? d_rs + o : nullptr, false);
+        if (rc != FW_OK) return rc;
+    }
+    return FW_OK;
+}
+
+int fw_solve_batched(fw_ctx *c, int32_t batch, int32_t n, double *rate, int32_t *next, int32_t *mid,
+                     int32_t *csT, int32_t *rs) {
+    if (n < 0 || batch < 0) return fail(FW_ERR_INVALID, "fw_solve_batched: negative size");
+    if (n == 0 || batch == 0) return FW_OK;
+    if (!rate || !next) return fail(FW_ERR_INVALID, "fw_solve_batched: null buffer");
+    if (!paths_args_ok(mid, csT, rs)) return fail(FW_ERR_INVALID, "mid/csT/rs: pass all three or none");
+    int rc = get_ctx(c, &c);
+    if (rc != FW_OK) return rc;
+    const size_t tot = (size_t)batch * n * n;
+    const bool paths = (mid != nullptr);
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        CU(cudaSetDevice(c->device));
+        if ((rc = c->s_rate.ensure(tot)) != FW_OK) return rc;
+        if ((rc = c->s_next.ensure(tot)) != FW_OK) return rc;
+        if (paths) {
+            if ((rc = c->s_mid.ensure(tot)) != FW_OK) return rc;
+            if ((rc = c->s_csT.ensure(tot)) != FW_OK) return rc;
+            if ((rc = c->s_rs.ensure(tot)) != FW_OK) return rc;
+        }
+        CU(cudaMemcpyAsync(c->s_rate.p, rate, tot * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->s_next.p, next, tot * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    rc = fw_solve_batched_device(c, batch, n, c->s_rate.p, c->s_next.p, paths ? c->s_mid.p : nullptr,
+                                 paths ? c->s_csT.p : nullptr, paths ? c->s_rs.p : nullptr);
+    if (rc != FW_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaMemcpyAsync(rate, c->s_rate.p, tot * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(next, c->s_next.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (paths) {
+        CU(cudaMemcpyAsync(mid, c->s_mid.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(csT, c->s_csT.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(rs, c->s_rs.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return FW_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+/*
+ * fwgpu.h -- C ABI of libfwgpu.so, the B200 (sm_100a) implementation of the
+ * matrix-optimisation hot path of jinilover/floydWarshall.
+ *
+ * The reference has no FFI today; the boundary this library sits under is the
+ * pure Haskell function
+ *     floydWarshall :: M.Map (Vertex, Vertex) Double -> Matrix RateEntry
+ *     (reference src/lib/Algorithms.hs:19-20  = runAlgo 0 . buildMatrix)
+ * whose body (runAlgo, src/lib/Algorithms.hs:42-61) is what fw_solve* replace.
+ * INTEGRATION.md shows the `foreign import ccall` stubs a maintainer adds.
+ *
+ * Dense encoding (row-major, n x n, caller-owned):
+ *   rate[i*n+j] = _bestRate (m ! i ! j)                   binary64
+ *   next[i*n+j] = index of (head _path), -1 if _path==[]  int32
+ * optional exact-path side tables (all int32, n x n, -1 = "initial edge"):
+ *   mid[i*n+j]  = k of the last step that replaced entry (i,j)
+ *   csT[i*n+k]  = mid of entry (i,k) when step k began
+ *   rs [k*n+j]  = mid of entry (k,j) when step k began
+ * (the reference's `_path = ikPath ++ kjPath`, Algorithms.hs:55, concatenates
+ * the sub-paths as they were AT STEP k; mid/csT/rs is the minimal record that
+ * reproduces it -- fw_paths expands it.)
+ *
+ * Semantics are exactly the reference loop: for k ascending, every entry with
+ * i != k, j != k, j != i is replaced iff  rate[i][j] < rate[i][k]*rate[k][j]
+ * (strict, one rounded binary64 multiply), taking next[i][k].  Results are
+ * bit-identical to that loop for every input in the domain below.
+ *
+ * Domain: rate entries must not be negative (NaN and +inf are tolerated and
+ * behave as in the reference); wherever rate[i][j] > 0 (i != j) next[i][j]
+ * must be >= 0 -- both hold for anything buildMatrix (Algorithms.hs:26-40)
+ * can produce from parser-validated input (Parsers.hs:40: rate > 0).
+ * Violations return FW_ERR_DOMAIN and leave the buffers untouched.
+ * The diagonal is never read nor written (Algorithms.hs:50,54).
+ *
+ * Errors: 0 = OK, negative = error; text via fw_last_error() (thread-local).
+ * No exceptions cross this boundary.  There is no CPU fallback: without a
+ * CUDA device every compute entry point returns FW_ERR_CUDA.
+ *
+ * Threading: a context serialises its own calls; distinct contexts may be
+ * used from distinct threads.  Entry points call cudaSetDevice themselves, so
+ * they may be called from any OS thread (GHC `safe` foreign calls).
+ */
+#ifndef FWGPU_H
+#define FWGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FW_OK 0
+#define FW_ERR_INVALID (-1) /* bad argument (null pointer, negative size, ...) */
+#define FW_ERR_CUDA (-2)    /* CUDA runtime failure / no device               */
+#define FW_ERR_DOMAIN (-3)  /* input outside the documented domain            */
+#define FW_ERR_NOMEM (-4)   /* device or host allocation failed               */
+#define FW_ERR_CAP (-5)     /* output capacity too small (fw_paths)           */
+
+#define FW_TILE 128 /* k-block size B and the largest "single tile" graph */
+
+typedef struct fw_ctx fw_ctx; /* opaque: device id, stream, workspace */
+
+/* ---- library / device ------------------------------------------------- */
+const char *fw_version(void);
+const char *fw_last_error(void);
+int fw_device_count(void);
+
+/* Create a context on `device` (>= 0).  Workspace grows on demand. */
+int fw_ctx_create(int device, fw_ctx **out);
+void fw_ctx_destroy(fw_ctx *ctx);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL
+ * restores the context's own stream. */
+int fw_ctx_set_stream(fw_ctx *ctx, void *cuda_stream);
+/* Kernel launches issued by the last solve on this context. */
+int64_t fw_ctx_last_launches(const fw_ctx *ctx);
+
+/* ---- replaces runAlgo (Algorithms.hs:42-61) ---------------------------- */
+/* Host buffers, in place.  mid/csT/rs may be NULL (all three or none).
+ * n == 0 succeeds and touches nothing (floydWarshall M.empty == V.empty,
+ * reference src/test/AlgorithmsTest.hs:62-64).  ctx may be NULL: a
+ * process-wide default context on device 0 is used. */
+int fw_solve(fw_ctx *ctx, int32_t n, double *rate, int32_t *next,
+             int32_t *mid, int32_t *csT, int32_t *rs);
+
+/* Same on DEVICE-resident buffers with leading dimension ld (elements),
+ * asynchronous on the context's stream.  Zero-copy when n is a multiple of
+ * FW_TILE (or n <= FW_TILE); otherwise the library works on a padded copy. */
+int fw_solve_device(fw_ctx *ctx, int32_t n, int64_t ld, double *d_rate,
+                    int32_t *d_next, int32_t *d_mid, int32_t *d_csT,
+                    int32_t *d_rs);
+
+/* `batch` independent graphs of the same n, batch-major contiguous
+ * (the FSM replay: one full solve per OutSync snapshot,
+ * reference src/lib/ProcessRequests.hs:82-84,97-102). */
+int fw_solve_batched(fw_ctx *ctx, int32_t batch, int32_t n, double *rate,
+                     int32_t *next, int32_t *mid, int32_t *csT, int32_t *rs);
+int fw_solve_batched_device(fw_ctx *ctx, int32_t batch, int32_t n,
+                            double *d_rate, int32_t *d_next, int32_t *d_mid,
+                            int32_t *d_csT, int32_t *d_rs);
+
+/* Block until everything queued on the context's stream has finished and
+ * report any asynchronous failure (incl. FW_ERR_DOMAIN of *_device calls). */
+int fw_ctx_synchronize(fw_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FWGPU_H */
