@@ -25,7 +25,7 @@ FW_TILE = 128
 SYMBOLS = (
     "fw_version", "fw_last_error", "fw_device_count", "fw_ctx_create", "fw_ctx_destroy",
     "fw_ctx_set_stream", "fw_ctx_last_launches", "fw_solve", "fw_solve_device", "fw_solve_batched",
-    "fw_solve_batched_device", "fw_ctx_synchronize",
+    "fw_solve_batched_device", "fw_ctx_synchronize", "fw_ctx_set_profiling", "fw_ctx_phase_ms",
 )
 
 
@@ -62,6 +62,10 @@ def load():
     L.fw_ctx_last_launches.argtypes = [vp]
     L.fw_ctx_synchronize.restype = ctypes.c_int
     L.fw_ctx_synchronize.argtypes = [vp]
+    L.fw_ctx_set_profiling.restype = ctypes.c_int
+    L.fw_ctx_set_profiling.argtypes = [vp, ctypes.c_int]
+    L.fw_ctx_phase_ms.restype = ctypes.c_int
+    L.fw_ctx_phase_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     L.fw_solve.restype = ctypes.c_int
     L.fw_solve.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.fw_solve_device.restype = ctypes.c_int
@@ -98,6 +102,16 @@ class Context:
 
     def synchronize(self):
         check(load().fw_ctx_synchronize(self._h))
+
+    def set_profiling(self, on: bool):
+        check(load().fw_ctx_set_profiling(self._h, 1 if on else 0))
+
+    def phase_ms(self):
+        """(ms[4], count[4]) of the last solve: tile, column panel, row panel, bulk."""
+        ms = (ctypes.c_double * 4)()
+        cnt = (ctypes.c_int64 * 4)()
+        check(load().fw_ctx_phase_ms(self._h, ms, cnt))
+        return list(ms), list(cnt)
 
     @property
     def last_launches(self) -> int:

@@ -16,6 +16,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/fwgpu.h"
 #include "fw_bulk.cuh"
@@ -124,6 +125,11 @@ struct fw_ctx {
     int *d_flag = nullptr;
     int *h_flag = nullptr;
     bool attrs_set = false;
+    // optional per-phase timing (CUDA events on the launching stream)
+    bool profiling = false;
+    struct Span { cudaEvent_t a, b; int phase; };
+    std::vector<Span> spans;      // spans of the last solve
+    std::vector<Span> pool;       // recycled events
 };
 
 namespace {
@@ -145,6 +151,27 @@ int set_kernel_attrs(fw_ctx *c) {
     CU(cudaFuncSetAttribute(fw::fw_bulk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
     c->attrs_set = true;
     return FW_OK;
+}
+
+// phase ids: 0 tile (phase 1), 1 column panel, 2 row panel, 3 bulk (phase 3)
+struct PhaseTimer {
+    fw_ctx *c; fw_ctx::Span s; bool on;
+    PhaseTimer(fw_ctx *c_, int phase) : c(c_), on(c_->profiling) {
+        if (!on) return;
+        if (!c->pool.empty()) { s = c->pool.back(); c->pool.pop_back(); }
+        else { cudaEventCreate(&s.a); cudaEventCreate(&s.b); }
+        s.phase = phase;
+        cudaEventRecord(s.a, c->stream);
+    }
+    ~PhaseTimer() {
+        if (!on) return;
+        cudaEventRecord(s.b, c->stream);
+        c->spans.push_back(s);
+    }
+};
+void recycle_spans(fw_ctx *c) {
+    for (auto &sp : c->spans) c->pool.push_back(sp);
+    c->spans.clear();
 }
 
 int grid_for(long long total, int sm_count) {
@@ -189,28 +216,37 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
         t.rate = rate; t.next = next; t.mid = mid; t.csT = csT; t.rs = rs;
         t.ld = ld; t.batch_stride = 0; t.b0 = b0; t.nv = FW_B;
         t.Cp = c->Cp.p; t.NCp = c->NCp.p; t.Rw = c->Rw.p; t.ldw = npad;
-        if (paths)
-            fw::fw_tile_kernel<true><<<1, 512, fw::tile_smem_bytes(true), c->stream>>>(t);
-        else
-            fw::fw_tile_kernel<false><<<1, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
+        {
+            PhaseTimer pt(c, 0);
+            if (paths)
+                fw::fw_tile_kernel<true><<<1, 512, fw::tile_smem_bytes(true), c->stream>>>(t);
+            else
+                fw::fw_tile_kernel<false><<<1, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
+        }
         c->launches++;
         if (nblk > 1) {
             fw::PanelArgs p;
             p.rate = rate; p.next = next; p.mid = mid; p.csT = csT; p.rs = rs;
             p.ld = ld; p.npad = npad; p.b0 = b0;
             p.Cp = c->Cp.p; p.NCp = c->NCp.p; p.Rw = c->Rw.p; p.ldw = npad;
-            if (paths) {
-                fw::fw_colpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
-                fw::fw_rowpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
-            } else {
-                fw::fw_colpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
-                fw::fw_rowpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+            {
+                PhaseTimer pt(c, 1);
+                if (paths) fw::fw_colpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+                else fw::fw_colpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+            }
+            {
+                PhaseTimer pt(c, 2);
+                if (paths) fw::fw_rowpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+                else fw::fw_rowpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
             }
             c->launches += 2;
             fw::BulkArgs g;
             g.rate = rate; g.next = next; g.mid = mid; g.ld = ld; g.npad = npad; g.b0 = b0;
             g.Cp = c->Cp.p; g.NCp = c->NCp.p; g.Rw = c->Rw.p; g.ldw = npad;
-            fw::fw_bulk_kernel<<<dim3(nt, nt), 128, 0, c->stream>>>(g);
+            {
+                PhaseTimer pt(c, 3);
+                fw::fw_bulk_kernel<<<dim3(nt, nt), 128, 0, c->stream>>>(g);
+            }
             c->launches++;
         }
         CU(cudaGetLastError());
@@ -231,10 +267,13 @@ int solve_tiles(fw_ctx *c, int batch, int n, long long ld, long long stride, dou
     t.rate = rate; t.next = next; t.mid = mid; t.csT = csT; t.rs = rs;
     t.ld = ld; t.batch_stride = stride; t.b0 = 0; t.nv = n;
     t.Cp = nullptr; t.NCp = nullptr; t.Rw = nullptr; t.ldw = 0;
-    if (paths)
-        fw::fw_tile_kernel<true><<<batch, 512, fw::tile_smem_bytes(true), c->stream>>>(t);
-    else
-        fw::fw_tile_kernel<false><<<batch, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
+    {
+        PhaseTimer pt(c, 0);
+        if (paths)
+            fw::fw_tile_kernel<true><<<batch, 512, fw::tile_smem_bytes(true), c->stream>>>(t);
+        else
+            fw::fw_tile_kernel<false><<<batch, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
+    }
     c->launches++;
     CU(cudaGetLastError());
     return FW_OK;
@@ -378,6 +417,28 @@ int fw_ctx_set_stream(fw_ctx *c, void *cuda_stream) {
 
 int64_t fw_ctx_last_launches(const fw_ctx *c) { return c ? c->launches : 0; }
 
+int fw_ctx_set_profiling(fw_ctx *c, int on) {
+    if (!c) return fail(FW_ERR_INVALID, "fw_ctx_set_profiling: null context");
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->profiling = (on != 0);
+    return FW_OK;
+}
+
+int fw_ctx_phase_ms(fw_ctx *c, double ms[4], int64_t count[4]) {
+    if (!c || !ms || !count) return fail(FW_ERR_INVALID, "fw_ctx_phase_ms: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 4; ++i) { ms[i] = 0.0; count[i] = 0; }
+    for (auto &sp : c->spans) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, sp.a, sp.b));
+        ms[sp.phase] += t;
+        count[sp.phase]++;
+    }
+    return FW_OK;
+}
+
 int fw_ctx_synchronize(fw_ctx *c) {
     int rc = get_ctx(c, &c);
     if (rc != FW_OK) return rc;
@@ -397,6 +458,7 @@ int fw_solve_device(fw_ctx *c, int32_t n, int64_t ld, double *d_rate, int32_t *d
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     c->launches = 0;
+    recycle_spans(c);
     return solve_device_locked(c, n, ld, d_rate, d_next, d_mid, d_csT, d_rs, true);
 }
 
@@ -410,6 +472,7 @@ int fw_solve(fw_ctx *c, int32_t n, double *rate, int32_t *next, int32_t *mid, in
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     c->launches = 0;
+    recycle_spans(c);
     if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
     const bool paths = (mid != nullptr);
     const int npad = (n <= FW_B) ? n : (n + FW_B - 1) / FW_B * FW_B;
@@ -471,6 +534,7 @@ int fw_solve_batched_device(fw_ctx *c, int32_t batch, int32_t n, double *d_rate,
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     c->launches = 0;
+    recycle_spans(c);
     if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
     const long long stride = (long long)n * n;
     if ((rc = validate_device(c, d_rate, d_next, n, stride, batch, n)) != FW_OK) return rc;

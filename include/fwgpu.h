@@ -74,6 +74,14 @@ int fw_ctx_set_stream(fw_ctx *ctx, void *cuda_stream);
 /* Kernel launches issued by the last solve on this context. */
 int64_t fw_ctx_last_launches(const fw_ctx *ctx);
 
+/* Optional per-phase timing: when on, every kernel launch of a solve is
+ * bracketed by CUDA events on the launching stream.  fw_ctx_phase_ms waits for
+ * the stream and returns, for the last solve, the summed device time and the
+ * launch count of: [0] diagonal-tile kernel, [1] column-panel kernel,
+ * [2] row-panel kernel, [3] bulk (phase 3) kernel. */
+int fw_ctx_set_profiling(fw_ctx *ctx, int on);
+int fw_ctx_phase_ms(fw_ctx *ctx, double ms[4], int64_t count[4]);
+
 /* ---- replaces runAlgo (Algorithms.hs:42-61) ---------------------------- */
 /* Host buffers, in place.  mid/csT/rs may be NULL (all three or none).
  * n == 0 succeeds and touches nothing (floydWarshall M.empty == V.empty,
