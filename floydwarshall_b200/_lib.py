@@ -57,7 +57,7 @@ def load():
     L.fw_ctx_destroy.restype = None
     L.fw_ctx_destroy.argtypes = [vp]
     L.fw_ctx_set_stream.restype = ctypes.c_int
-    L.fw_ctx_set_stream.argtypes = [vp, vp]
+    L.fw_ctx_set_stream.argtypes = [vp, vp, ctypes.c_int]
     L.fw_ctx_last_launches.restype = i64
     L.fw_ctx_last_launches.argtypes = [vp]
     L.fw_ctx_synchronize.restype = ctypes.c_int
@@ -98,7 +98,12 @@ class Context:
         return self._h
 
     def set_stream(self, cuda_stream: int | None):
-        check(load().fw_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream or 0)))
+        """cuda_stream: a cudaStream_t handle as int (0 = legacy default stream), or None for
+        the context's own stream."""
+        if cuda_stream is None:
+            check(load().fw_ctx_set_stream(self._h, None, 0))
+        else:
+            check(load().fw_ctx_set_stream(self._h, ctypes.c_void_p(cuda_stream), 1))
 
     def synchronize(self):
         check(load().fw_ctx_synchronize(self._h))

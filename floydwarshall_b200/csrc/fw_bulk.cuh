@@ -3,7 +3,11 @@
 // order against the two read-only snapshot panels
 //     n = Cp[i][kk] * Rw[kk][j];   if (R[i][j] < n) { R[i][j] = n; mid = kk; }
 // and resolves its next-hop once, at the end:  NX[i][j] = NCp[i][mid].
-// This is >99 % of the work of a large solve and is FP64-pipe/issue bound.
+// This is >99 % of the work of a large solve.  Relaxations fire rarely (about
+// 7 times per ENTRY over a whole solve, i.e. ~7/N of them), so each k step
+// first runs a 1-DFMA-per-relaxation filter that proves "nothing fires here"
+// for the whole warp and only falls into the exact mul/compare/select path
+// when some lane has a candidate.  The fast path is FP64-pipe bound (DFMA).
 //
 // CTA = 128 threads, 64x64 output tile held in registers (8 rows x 4 columns
 // per thread + 32 mids); the panels stream through shared memory in k-chunks
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(128, 3) fw_bulk_kernel(BulkArgs a) {
             cp_async_wait<0>();
         }
         __syncthreads();
-#pragma unroll
+#pragma unroll 2
         for (int k2 = 0; k2 < BULK_KC / 2; ++k2) {
             double2 a2[8];
 #pragma unroll
@@ -105,15 +109,34 @@ __global__ void __launch_bounds__(128, 3) fw_bulk_kernel(BulkArgs a) {
                 const int kk = k2 * 2 + h;
                 const double2 b01 = *reinterpret_cast<const double2 *>(&Bs[buf][kk][tx * 2]);
                 const double2 b23 = *reinterpret_cast<const double2 *>(&Bs[buf][kk][32 + tx * 2]);
-                const int kloc = ch * BULK_KC + kk;
+                // Filter (1 DFMA per relaxation): with round-toward-minus-infinity,
+                //   sign(fma(a, b, -o)) is clear  <=>  exact(a*b) > o  (or a positive-signed NaN),
+                // and exact(a*b) <= o implies RN(a*b) <= o, i.e. the reference's strict test
+                // o < a*b (Algorithms.hs:55,61) cannot fire.  An exact tie gives -0 under RM.
+                // So "all sign bits set" proves that none of these 32 relaxations fires.
+                int acc = -1;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const double av = h ? a2[r].y : a2[r].x;
-                    double n;
-                    n = av * b01.x; if (o[r][0] < n) { o[r][0] = n; m[r][0] = kloc; }
-                    n = av * b01.y; if (o[r][1] < n) { o[r][1] = n; m[r][1] = kloc; }
-                    n = av * b23.x; if (o[r][2] < n) { o[r][2] = n; m[r][2] = kloc; }
-                    n = av * b23.y; if (o[r][3] < n) { o[r][3] = n; m[r][3] = kloc; }
+                    const double d0 = __fma_rd(av, b01.x, -o[r][0]);
+                    const double d1 = __fma_rd(av, b01.y, -o[r][1]);
+                    const double d2 = __fma_rd(av, b23.x, -o[r][2]);
+                    const double d3 = __fma_rd(av, b23.y, -o[r][3]);
+                    acc &= __double2hiint(d0) & __double2hiint(d1);
+                    acc &= __double2hiint(d2) & __double2hiint(d3);
+                }
+                if (__builtin_expect(__any_sync(0xffffffffu, acc >= 0), 0)) {
+                    // exact path: one rounded multiply, strict compare, ascending k
+                    const int kloc = ch * BULK_KC + kk;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const double av = h ? a2[r].y : a2[r].x;
+                        double n;
+                        n = av * b01.x; if (o[r][0] < n) { o[r][0] = n; m[r][0] = kloc; }
+                        n = av * b01.y; if (o[r][1] < n) { o[r][1] = n; m[r][1] = kloc; }
+                        n = av * b23.x; if (o[r][2] < n) { o[r][2] = n; m[r][2] = kloc; }
+                        n = av * b23.y; if (o[r][3] < n) { o[r][3] = n; m[r][3] = kloc; }
+                    }
                 }
             }
         }

@@ -408,10 +408,10 @@ void fw_ctx_destroy(fw_ctx *c) {
     delete c;
 }
 
-int fw_ctx_set_stream(fw_ctx *c, void *cuda_stream) {
+int fw_ctx_set_stream(fw_ctx *c, void *cuda_stream, int external) {
     if (!c) return fail(FW_ERR_INVALID, "fw_ctx_set_stream: null context");
     std::lock_guard<std::mutex> lk(c->mu);
-    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    c->stream = external ? (cudaStream_t)cuda_stream : c->own_stream;
     return FW_OK;
 }
 

@@ -68,9 +68,10 @@ int fw_device_count(void);
 /* Create a context on `device` (>= 0).  Workspace grows on demand. */
 int fw_ctx_create(int device, fw_ctx **out);
 void fw_ctx_destroy(fw_ctx *ctx);
-/* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL
- * restores the context's own stream. */
-int fw_ctx_set_stream(fw_ctx *ctx, void *cuda_stream);
+/* external != 0: launch on the caller's cudaStream_t `cuda_stream` (a NULL
+ * handle is the legacy default stream, which is what torch's current stream
+ * usually is); external == 0: back to the context's own stream. */
+int fw_ctx_set_stream(fw_ctx *ctx, void *cuda_stream, int external);
 /* Kernel launches issued by the last solve on this context. */
 int64_t fw_ctx_last_launches(const fw_ctx *ctx);
 

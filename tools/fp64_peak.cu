@@ -44,10 +44,10 @@ __global__ void __launch_bounds__(256) k_dmul(double *out, int iters, double a) 
 
 template <bool MID>
 __global__ void __launch_bounds__(128, 3) k_relax(double *out, int *outm, int iters, const double *src) {
-    __shared__ __align__(16) double As[64][18];
-    __shared__ __align__(16) double Bs[16][64];
+    __shared__ __align__(16) double As[2][64][18];
+    __shared__ __align__(16) double Bs[2][16][64];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-    for (int i = tid; i < 64 * 16; i += 128) { As[i >> 4][i & 15] = src[i]; Bs[i >> 6][i & 63] = src[1024 + i]; }
+    for (int i = tid; i < 2 * 64 * 16; i += 128) { As[i >> 10][(i >> 4) & 63][i & 15] = src[i & 1023]; Bs[i >> 10][(i >> 6) & 15][i & 63] = src[1024 + (i & 1023)]; }
     __syncthreads();
     double o[8][4];
     int m[8][4];
@@ -55,17 +55,19 @@ __global__ void __launch_bounds__(128, 3) k_relax(double *out, int *outm, int it
     for (int r = 0; r < 8; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) { o[r][c] = 0.97 + 1e-4 * (r + c + tx); m[r][c] = -1; }
+#pragma unroll 1
     for (int it = 0; it < iters; ++it) {
+        const int buf = it & 1;
 #pragma unroll
         for (int k2 = 0; k2 < 8; ++k2) {
             double2 a2[8];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) a2[r] = *reinterpret_cast<const double2 *>(&As[r * 8 + ty][k2 * 2]);
+            for (int r = 0; r < 8; ++r) a2[r] = *reinterpret_cast<const double2 *>(&As[buf][r * 8 + ty][k2 * 2]);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int kk = k2 * 2 + h;
-                const double2 b01 = *reinterpret_cast<const double2 *>(&Bs[kk][tx * 2]);
-                const double2 b23 = *reinterpret_cast<const double2 *>(&Bs[kk][32 + tx * 2]);
+                const double2 b01 = *reinterpret_cast<const double2 *>(&Bs[buf][kk][tx * 2]);
+                const double2 b23 = *reinterpret_cast<const double2 *>(&Bs[buf][kk][32 + tx * 2]);
                 const int kloc = it * 16 + kk;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
