@@ -26,6 +26,7 @@ SYMBOLS = (
     "fw_version", "fw_last_error", "fw_device_count", "fw_ctx_create", "fw_ctx_destroy",
     "fw_ctx_set_stream", "fw_ctx_last_launches", "fw_solve", "fw_solve_device", "fw_solve_batched",
     "fw_solve_batched_device", "fw_ctx_synchronize", "fw_ctx_set_profiling", "fw_ctx_phase_ms",
+    "fw_ctx_phase_spans", "fw_shard_validate", "fw_shard_pivot", "fw_shard_update",
 )
 
 
@@ -66,6 +67,14 @@ def load():
     L.fw_ctx_set_profiling.argtypes = [vp, ctypes.c_int]
     L.fw_ctx_phase_ms.restype = ctypes.c_int
     L.fw_ctx_phase_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
+    L.fw_ctx_phase_spans.restype = i64
+    L.fw_ctx_phase_spans.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), i64]
+    L.fw_shard_validate.restype = ctypes.c_int
+    L.fw_shard_validate.argtypes = [vp, i32, i32, i32, i64, vp, vp]
+    L.fw_shard_pivot.restype = ctypes.c_int
+    L.fw_shard_pivot.argtypes = [vp, i32, i32, i32, i64, vp, vp, i32, vp]
+    L.fw_shard_update.restype = ctypes.c_int
+    L.fw_shard_update.argtypes = [vp, i32, i32, i32, i64, vp, vp, i32, vp]
     L.fw_solve.restype = ctypes.c_int
     L.fw_solve.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.fw_solve_device.restype = ctypes.c_int
@@ -117,6 +126,16 @@ class Context:
         cnt = (ctypes.c_int64 * 4)()
         check(load().fw_ctx_phase_ms(self._h, ms, cnt))
         return list(ms), list(cnt)
+
+    def phase_spans(self, phase: int):
+        """Per-launch ms of one phase (0 tile, 1 col panel, 2 row panel, 3 bulk) of the last solve."""
+        L = load()
+        n = int(L.fw_ctx_phase_spans(self._h, phase, None, 0))
+        if n < 0:
+            check(n)
+        buf = (ctypes.c_double * max(n, 1))()
+        L.fw_ctx_phase_spans(self._h, phase, buf, n)
+        return list(buf)[:n]
 
     @property
     def last_launches(self) -> int:

@@ -28,8 +28,10 @@ struct PanelArgs {
     int32_t *csT;   // PATHS only
     int32_t *rs;    // PATHS only
     long long ld;
-    int npad;       // padded matrix order (multiple of FW_B)
-    int b0;         // first pivot of the k-block
+    int npad;       // padded matrix order = number of columns (multiple of FW_B)
+    int b0;         // first pivot of the k-block (global index)
+    int rows;       // rows held by this shard (== npad when unsharded)
+    int blk_r0;     // LOCAL row of pivot b0 if this shard holds the k-block rows, else INT_MAX
     double *Cp;     // N x B column snapshots
     int32_t *NCp;
     double *Rw;     // B x N row snapshots
@@ -53,10 +55,10 @@ __global__ void __launch_bounds__(512, 1) fw_colpanel_kernel(PanelArgs a) {
     __syncthreads();
 
     const int job = tid >> 4, l = tid & 15;
-    const int nrows = a.npad - FW_B;
+    const int nrows = a.rows - (a.blk_r0 < a.rows ? FW_B : 0);
     for (int g = blockIdx.x; g * 32 < nrows; g += gridDim.x) {
         const int rp = g * 32 + job;
-        const int i = rp < b0 ? rp : rp + FW_B;
+        const int i = rp < a.blk_r0 ? rp : rp + FW_B;   // local row, skipping the k-block rows
         const long long off = (long long)i * a.ld + b0 + l * 8;
         double y[8], cs[8];
         int nx[8], ncs[8], md[8], mcs[8];
@@ -134,10 +136,10 @@ __global__ void __launch_bounds__(512, 1) fw_rowpanel_kernel(PanelArgs a) {
     double *Fs = reinterpret_cast<double *>(smem_raw);
     const int tid = threadIdx.x;
     const int b0 = a.b0;
-    // factor matrix F[kk][i] = Cd[i][kk] = Cp[(b0+i)*B + kk]   (transposed fill)
+    // factor matrix F[kk][i] = Cd[i][kk] = Cp[(blk_r0+i)*B + kk]   (transposed fill; owner shard only)
     for (int idx = tid; idx < 128 * 128; idx += 512) {
         const int i = idx >> 7, kk = idx & 127;
-        Fs[kk * PANEL_FP + swz128(i)] = a.Cp[(long long)(b0 + i) * FW_B + kk];
+        Fs[kk * PANEL_FP + swz128(i)] = a.Cp[(long long)(a.blk_r0 + i) * FW_B + kk];
     }
     __syncthreads();
 
@@ -146,7 +148,7 @@ __global__ void __launch_bounds__(512, 1) fw_rowpanel_kernel(PanelArgs a) {
     for (int g = blockIdx.x; g * 32 < ncols; g += gridDim.x) {
         const int jp = g * 32 + job;
         const int j = jp < b0 ? jp : jp + FW_B;
-        const long long off = (long long)(b0 + l * 8) * a.ld + j;  // + c*ld
+        const long long off = (long long)(a.blk_r0 + l * 8) * a.ld + j;  // + c*ld
         double x[8], snap[8];
         int m[8], mo[8], msnap[8];
 #pragma unroll
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(512, 1) fw_rowpanel_kernel(PanelArgs a) {
             const long long o = off + (long long)c * a.ld;
             if (m[c] >= 0) {
                 a.rate[o] = x[c];
-                a.next[o] = a.NCp[(long long)(b0 + l * 8 + c) * FW_B + m[c]];
+                a.next[o] = a.NCp[(long long)(a.blk_r0 + l * 8 + c) * FW_B + m[c]];
                 if (PATHS) a.mid[o] = b0 + m[c];
             }
             a.Rw[(long long)(l * 8 + c) * a.ldw + j] = snap[c];

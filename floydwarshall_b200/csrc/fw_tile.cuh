@@ -31,7 +31,8 @@ struct TileArgs {
     int32_t *rs;            // PATHS only
     long long ld;           // leading dimension, elements
     long long batch_stride; // elements between graphs (batched mode), else 0
-    int b0;                 // tile origin (row == column)
+    int b0;                 // tile origin: global column (== global row of the pivots)
+    int r0;                 // tile origin: LOCAL row inside this shard (== b0 when unsharded)
     int nv;                 // valid rows/cols inside the tile (1..128)
     double *Cp;             // snapshot outputs; null in batched mode
     int32_t *NCp;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(512, 1) fw_tile_kernel(TileArgs a) {
     const int ty = tid >> 4, tx = tid & 15;
     const int nv = a.nv;
     const long long ld = a.ld;
-    const long long goff = (long long)blockIdx.x * a.batch_stride + (long long)a.b0 * ld + a.b0;
+    const long long goff = (long long)blockIdx.x * a.batch_stride + (long long)a.r0 * ld + a.b0;
     double *R = a.rate + goff;
     int32_t *NX = a.next + goff;
 
@@ -104,8 +105,8 @@ __global__ void __launch_bounds__(512, 1) fw_tile_kernel(TileArgs a) {
                 // snapshots for the other phases (diag mode only)
                 if (a.Cp != nullptr) {
                     if (tid < 128) {
-                        a.Cp[(long long)(a.b0 + tid) * FW_B + k] = cb[tid];
-                        a.NCp[(long long)(a.b0 + tid) * FW_B + k] = NXs[tid * TILE_NXP + k];
+                        a.Cp[(long long)(a.r0 + tid) * FW_B + k] = cb[tid];
+                        a.NCp[(long long)(a.r0 + tid) * FW_B + k] = NXs[tid * TILE_NXP + k];
                     } else if (tid < 256) {
                         const int j = tid - 128;
                         a.Rw[(long long)k * a.ldw + a.b0 + j] = rb[swz128(j)];

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -46,15 +47,16 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 // ---------------------------------------------------------------- helper kernels
 // flag bit 0: negative rate; bit 1: rate > 0 (off-diagonal) with next < 0
+// Each of `batch` graphs is rows x n (rows == n unless it is a row shard starting at global row row0).
 __global__ void fw_validate_kernel(const double *rate, const int32_t *next, long long ld, long long stride,
-                                   int n, long long total, int *flag) {
+                                   int rows, int n, int row0, long long total, int *flag) {
     int bad = 0;
-    const long long nn = (long long)n * n;
+    const long long nn = (long long)rows * n;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
         const long long g = e / nn, rem = e - g * nn;
         const int i = (int)(rem / n), j = (int)(rem - (long long)i * n);
-        if (i == j) continue;  // the diagonal is never read (Algorithms.hs:50,54)
+        if (row0 + i == j) continue;  // the diagonal is never read (Algorithms.hs:50,54)
         const long long off = g * stride + (long long)i * ld + j;
         const double v = rate[off];
         if (v < 0.0) bad |= 1;
@@ -125,6 +127,7 @@ struct fw_ctx {
     int *d_flag = nullptr;
     int *h_flag = nullptr;
     bool attrs_set = false;
+    int bulk_window = 1;   // k steps filtered per warp vote in fw_bulk_kernel (experiment knob: FW_BULK_WINDOW)
     // optional per-phase timing (CUDA events on the launching stream)
     bool profiling = false;
     struct Span { cudaEvent_t a, b; int phase; };
@@ -148,7 +151,13 @@ int set_kernel_attrs(fw_ctx *c) {
                             (int)fw::panel_smem_bytes()));
     CU(cudaFuncSetAttribute(fw::fw_rowpanel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)fw::panel_smem_bytes()));
-    CU(cudaFuncSetAttribute(fw::fw_bulk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 50));
+    CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::bulk_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::bulk_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (const char *e = getenv("FW_BULK_WINDOW")) c->bulk_window = atoi(e) == 2 ? 2 : 1;
     c->attrs_set = true;
     return FW_OK;
 }
@@ -184,11 +193,12 @@ int grid_for(long long total, int sm_count) {
 
 // Domain check (synchronises the stream once).
 int validate_device(fw_ctx *c, const double *rate, const int32_t *next, long long ld, long long stride,
-                    int batch, int n) {
+                    int batch, int n, int rows = -1, int row0 = 0) {
+    if (rows < 0) rows = n;
     CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
-    const long long total = (long long)batch * n * n;
-    fw_validate_kernel<<<grid_for(total, c->sm_count), 256, 0, c->stream>>>(rate, next, ld, stride, n, total,
-                                                                             c->d_flag);
+    const long long total = (long long)batch * rows * n;
+    fw_validate_kernel<<<grid_for(total, c->sm_count), 256, 0, c->stream>>>(rate, next, ld, stride, rows, n, row0,
+                                                                             total, c->d_flag);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -214,7 +224,7 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
         const int b0 = b * FW_B;
         fw::TileArgs t;
         t.rate = rate; t.next = next; t.mid = mid; t.csT = csT; t.rs = rs;
-        t.ld = ld; t.batch_stride = 0; t.b0 = b0; t.nv = FW_B;
+        t.ld = ld; t.batch_stride = 0; t.b0 = b0; t.r0 = b0; t.nv = FW_B;
         t.Cp = c->Cp.p; t.NCp = c->NCp.p; t.Rw = c->Rw.p; t.ldw = npad;
         {
             PhaseTimer pt(c, 0);
@@ -227,7 +237,7 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
         if (nblk > 1) {
             fw::PanelArgs p;
             p.rate = rate; p.next = next; p.mid = mid; p.csT = csT; p.rs = rs;
-            p.ld = ld; p.npad = npad; p.b0 = b0;
+            p.ld = ld; p.npad = npad; p.b0 = b0; p.rows = npad; p.blk_r0 = b0;
             p.Cp = c->Cp.p; p.NCp = c->NCp.p; p.Rw = c->Rw.p; p.ldw = npad;
             {
                 PhaseTimer pt(c, 1);
@@ -242,10 +252,14 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
             c->launches += 2;
             fw::BulkArgs g;
             g.rate = rate; g.next = next; g.mid = mid; g.ld = ld; g.npad = npad; g.b0 = b0;
+            g.rows = npad; g.row0 = 0; g.blk_r0 = b0;
             g.Cp = c->Cp.p; g.NCp = c->NCp.p; g.Rw = c->Rw.p; g.ldw = npad;
             {
                 PhaseTimer pt(c, 3);
-                fw::fw_bulk_kernel<<<dim3(nt, nt), 128, 0, c->stream>>>(g);
+                if (c->bulk_window == 2)
+                    fw::fw_bulk_kernel<2><<<dim3(nt, nt), 128, fw::bulk_smem_bytes(), c->stream>>>(g);
+                else
+                    fw::fw_bulk_kernel<1><<<dim3(nt, nt), 128, fw::bulk_smem_bytes(), c->stream>>>(g);
             }
             c->launches++;
         }
@@ -265,7 +279,7 @@ int solve_tiles(fw_ctx *c, int batch, int n, long long ld, long long stride, dou
     const bool paths = (mid != nullptr);
     fw::TileArgs t;
     t.rate = rate; t.next = next; t.mid = mid; t.csT = csT; t.rs = rs;
-    t.ld = ld; t.batch_stride = stride; t.b0 = 0; t.nv = n;
+    t.ld = ld; t.batch_stride = stride; t.b0 = 0; t.r0 = 0; t.nv = n;
     t.Cp = nullptr; t.NCp = nullptr; t.Rw = nullptr; t.ldw = 0;
     {
         PhaseTimer pt(c, 0);
@@ -422,6 +436,24 @@ int fw_ctx_set_profiling(fw_ctx *c, int on) {
     std::lock_guard<std::mutex> lk(c->mu);
     c->profiling = (on != 0);
     return FW_OK;
+}
+
+int64_t fw_ctx_phase_spans(fw_ctx *c, int phase, double *ms, int64_t cap) {
+    if (!c || phase < 0 || phase > 3 || (!ms && cap > 0)) return fail(FW_ERR_INVALID, "fw_ctx_phase_spans: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
+        return fail(FW_ERR_CUDA, "fw_ctx_phase_spans: stream synchronize failed");
+    int64_t n = 0;
+    for (auto &sp : c->spans) {
+        if (sp.phase != phase) continue;
+        if (n < cap) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, sp.a, sp.b);
+            ms[n] = t;
+        }
+        ++n;
+    }
+    return n;
 }
 
 int fw_ctx_phase_ms(fw_ctx *c, double ms[4], int64_t count[4]) {
@@ -590,6 +622,107 @@ int fw_solve_batched(fw_ctx *c, int32_t batch, int32_t n, double *rate, int32_t 
         CU(cudaMemcpyAsync(rs, c->s_rs.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
     }
     CU(cudaStreamSynchronize(c->stream));
+    return FW_OK;
+}
+
+/* ---- row-sharded building blocks (multi-GPU) ------------------------------- */
+static int shard_args_ok(int32_t n, int32_t row0, int32_t rows, int64_t ld, const void *rate, const void *next,
+                         int32_t b0, const void *Rw) {
+    if (n <= 0 || rows <= 0 || row0 < 0 || b0 < 0 || !rate || !next || !Rw) return 0;
+    if (n % FW_B || rows % FW_B || row0 % FW_B || b0 % FW_B) return 0;
+    if (row0 + rows > n || b0 >= n || ld < n || ld % 4) return 0;
+    if (((uintptr_t)rate & 15) || ((uintptr_t)next & 15) || ((uintptr_t)Rw & 15)) return 0;
+    return 1;
+}
+
+int fw_shard_validate(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, const double *d_rate,
+                      const int32_t *d_next) {
+    if (!c || n <= 0 || rows <= 0 || !d_rate || !d_next || ld < n)
+        return fail(FW_ERR_INVALID, "fw_shard_validate: bad argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    return validate_device(c, d_rate, d_next, ld, 0, 1, n, rows, row0);
+}
+
+int fw_shard_pivot(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
+                   int32_t *d_next, int32_t b0, double *d_Rw) {
+    if (!c || !shard_args_ok(n, row0, rows, ld, d_rate, d_next, b0, d_Rw))
+        return fail(FW_ERR_INVALID, "fw_shard_pivot: bad argument (sizes must be multiples of 128, 16-byte aligned)");
+    if (b0 < row0 || b0 >= row0 + rows) return fail(FW_ERR_INVALID, "fw_shard_pivot: this shard does not own k-block b0");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
+    if ((rc = c->Cp.ensure((size_t)rows * FW_B)) != FW_OK) return rc;
+    if ((rc = c->NCp.ensure((size_t)rows * FW_B)) != FW_OK) return rc;
+    c->launches = 0;
+    recycle_spans(c);
+    const int blk_r0 = b0 - row0;
+    fw::TileArgs t;
+    t.rate = d_rate; t.next = d_next; t.mid = nullptr; t.csT = nullptr; t.rs = nullptr;
+    t.ld = ld; t.batch_stride = 0; t.b0 = b0; t.r0 = blk_r0; t.nv = FW_B;
+    t.Cp = c->Cp.p; t.NCp = c->NCp.p; t.Rw = d_Rw; t.ldw = n;
+    {
+        PhaseTimer pt(c, 0);
+        fw::fw_tile_kernel<false><<<1, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
+    }
+    c->launches++;
+    if (n > FW_B) {
+        fw::PanelArgs p;
+        p.rate = d_rate; p.next = d_next; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
+        p.ld = ld; p.npad = n; p.b0 = b0; p.rows = rows; p.blk_r0 = blk_r0;
+        p.Cp = c->Cp.p; p.NCp = c->NCp.p; p.Rw = d_Rw; p.ldw = n;
+        const int njobs32 = (n - FW_B) / 32;
+        const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
+        PhaseTimer pt(c, 2);
+        fw::fw_rowpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    return FW_OK;
+}
+
+int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
+                    int32_t *d_next, int32_t b0, const double *d_Rw) {
+    if (!c || !shard_args_ok(n, row0, rows, ld, d_rate, d_next, b0, d_Rw))
+        return fail(FW_ERR_INVALID, "fw_shard_update: bad argument (sizes must be multiples of 128, 16-byte aligned)");
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
+    if ((rc = c->Cp.ensure((size_t)rows * FW_B)) != FW_OK) return rc;
+    if ((rc = c->NCp.ensure((size_t)rows * FW_B)) != FW_OK) return rc;
+    const bool owner = (b0 >= row0 && b0 < row0 + rows);
+    if (!owner) { c->launches = 0; recycle_spans(c); }   // the owner keeps counting after fw_shard_pivot
+    const int blk_r0 = owner ? b0 - row0 : 0x7fffffff;
+    const int rows_out = rows - (owner ? FW_B : 0);
+    if (rows_out > 0 && n > FW_B) {
+        fw::PanelArgs p;
+        p.rate = d_rate; p.next = d_next; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
+        p.ld = ld; p.npad = n; p.b0 = b0; p.rows = rows; p.blk_r0 = blk_r0;
+        p.Cp = c->Cp.p; p.NCp = c->NCp.p; p.Rw = const_cast<double *>(d_Rw); p.ldw = n;
+        const int njobs32 = rows_out / 32;
+        const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
+        {
+            PhaseTimer pt(c, 1);
+            fw::fw_colpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+        }
+        c->launches++;
+        fw::BulkArgs g;
+        g.rate = d_rate; g.next = d_next; g.mid = nullptr; g.ld = ld; g.npad = n; g.b0 = b0;
+        g.rows = rows; g.row0 = row0; g.blk_r0 = blk_r0;
+        g.Cp = c->Cp.p; g.NCp = c->NCp.p; g.Rw = d_Rw; g.ldw = n;
+        const dim3 grid(n / fw::BULK_T - FW_B / fw::BULK_T, rows_out / fw::BULK_T);
+        {
+            PhaseTimer pt(c, 3);
+            if (c->bulk_window == 2)
+                fw::fw_bulk_kernel<2><<<grid, 128, fw::bulk_smem_bytes(), c->stream>>>(g);
+            else
+                fw::fw_bulk_kernel<1><<<grid, 128, fw::bulk_smem_bytes(), c->stream>>>(g);
+        }
+        c->launches++;
+    }
+    CU(cudaGetLastError());
     return FW_OK;
 }
 

@@ -82,6 +82,9 @@ int64_t fw_ctx_last_launches(const fw_ctx *ctx);
  * [2] row-panel kernel, [3] bulk (phase 3) kernel. */
 int fw_ctx_set_profiling(fw_ctx *ctx, int on);
 int fw_ctx_phase_ms(fw_ctx *ctx, double ms[4], int64_t count[4]);
+/* Per-launch device times (ms, launch order) of one phase of the last solve;
+ * returns the number of launches of that phase (may exceed cap), < 0 on error. */
+int64_t fw_ctx_phase_spans(fw_ctx *ctx, int phase, double *ms, int64_t cap);
 
 /* ---- replaces runAlgo (Algorithms.hs:42-61) ---------------------------- */
 /* Host buffers, in place.  mid/csT/rs may be NULL (all three or none).
@@ -106,6 +109,23 @@ int fw_solve_batched(fw_ctx *ctx, int32_t batch, int32_t n, double *rate,
 int fw_solve_batched_device(fw_ctx *ctx, int32_t batch, int32_t n,
                             double *d_rate, int32_t *d_next, int32_t *d_mid,
                             int32_t *d_csT, int32_t *d_rs);
+
+/* ---- row-sharded building blocks (one shard per GPU) ----------------------
+ * The multi-GPU solve keeps rows [row0, row0+rows) of the n x n
+ * matrix on each GPU (n, row0, rows multiples of FW_TILE; ld % 4 == 0).  For
+ * every k-block b0 = 0, 128, ...:
+ *   owner of rows [b0, b0+128):  fw_shard_pivot  -> fills d_Rw (128 x n, the
+ *        step-k snapshots of the pivot rows) from its diagonal tile + row panel
+ *   caller broadcasts d_Rw from the owner to all ranks (NCCL)
+ *   every rank:                  fw_shard_update -> column panel + bulk on its rows
+ * Next-hops never cross ranks (NX[i][j] <- NX[i][k] is row-local).  All calls
+ * are asynchronous on the context's stream.  No exact-path tables here. */
+int fw_shard_validate(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
+                      const double *d_rate, const int32_t *d_next);
+int fw_shard_pivot(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
+                   double *d_rate, int32_t *d_next, int32_t b0, double *d_Rw);
+int fw_shard_update(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
+                    double *d_rate, int32_t *d_next, int32_t b0, const double *d_Rw);
 
 /* Block until everything queued on the context's stream has finished and
  * report any asynchronous failure (incl. FW_ERR_DOMAIN of *_device calls). */

@@ -42,6 +42,72 @@ __global__ void __launch_bounds__(256) k_dmul(double *out, int iters, double a) 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+__global__ void __launch_bounds__(256) k_dfma_rm(double *out, int iters, double a, double b) {
+    double x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = __fma_rd(x[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// the bulk kernel's fast path alone: 32 DFMA.RM + sign-word AND tree + warp vote per k step
+template <int CTAS>
+__global__ void __launch_bounds__(128, CTAS) k_filter(double *out, int *outm, int iters, const double *src) {
+    __shared__ __align__(16) double As[2][64][18];
+    __shared__ __align__(16) double Bs[2][16][64];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    for (int i = tid; i < 2 * 64 * 16; i += 128) { As[i >> 10][(i >> 4) & 63][i & 15] = src[i & 1023]; Bs[i >> 10][(i >> 6) & 15][i & 63] = src[1024 + (i & 1023)]; }
+    __syncthreads();
+    double o[8][4];
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[r][c] = 1.3 + 1e-4 * (r + c + tx);   // above every product: the filter never fires
+    int fired = 0;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+        const int buf = it & 1;
+#pragma unroll 4
+        for (int kk = 0; kk < 16; ++kk) {
+            double av[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) av[r] = As[buf][r * 8 + ty][kk];
+            const double2 b01 = *reinterpret_cast<const double2 *>(&Bs[buf][kk][tx * 2]);
+            const double2 b23 = *reinterpret_cast<const double2 *>(&Bs[buf][kk][32 + tx * 2]);
+            int hi[8][4];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                hi[r][0] = __double2hiint(__fma_rd(av[r], b01.x, -o[r][0]));
+                hi[r][1] = __double2hiint(__fma_rd(av[r], b01.y, -o[r][1]));
+                hi[r][2] = __double2hiint(__fma_rd(av[r], b23.x, -o[r][2]));
+                hi[r][3] = __double2hiint(__fma_rd(av[r], b23.y, -o[r][3]));
+            }
+            int accr[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) accr[r] = (hi[r][0] & hi[r][1]) & (hi[r][2] & hi[r][3]);
+            const int acc = ((accr[0] & accr[1]) & (accr[2] & accr[3])) & ((accr[4] & accr[5]) & (accr[6] & accr[7]));
+            if (__builtin_expect(__any_sync(0xffffffffu, acc >= 0), 0)) {
+                fired++;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) o[r][0] += 1e-9;   // keep o live/mutable
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s += o[r][c];
+    out[blockIdx.x * blockDim.x + tid] = s;
+    outm[blockIdx.x * blockDim.x + tid] = fired;
+}
+
 template <bool MID>
 __global__ void __launch_bounds__(128, 3) k_relax(double *out, int *outm, int iters, const double *src) {
     __shared__ __align__(16) double As[2][64][18];
@@ -124,19 +190,26 @@ int main() {
     const int g1 = sms * 8;
     double t_dfma = time_ms([&] { k_dfma<<<g1, 256>>>(out, it1, 0.999999, 1e-9); }, 5);
     double t_dmul = time_ms([&] { k_dmul<<<g1, 256>>>(out, it1, 0.9999999); }, 5);
+    double t_dfma_rm = time_ms([&] { k_dfma_rm<<<g1, 256>>>(out, it1, 0.999999, 1e-9); }, 5);
     const double n1 = (double)g1 * 256 * 16 * it1;
     const int it2 = 2048;
     const int g2 = sms * 3 * 4;
     double t_rel = time_ms([&] { k_relax<true><<<g2, 128>>>(out, outm, it2, src); }, 5);
     double t_relv = time_ms([&] { k_relax<false><<<g2, 128>>>(out, outm, it2, src); }, 5);
     const double n2 = (double)g2 * 128 * 32 * 16 * it2;
+    double t_f2 = time_ms([&] { k_filter<2><<<sms * 2 * 4, 128>>>(out, outm, it2, src); }, 5);
+    double t_f3 = time_ms([&] { k_filter<3><<<sms * 3 * 4, 128>>>(out, outm, it2, src); }, 5);
+    double t_f4 = time_ms([&] { k_filter<4><<<sms * 4 * 4, 128>>>(out, outm, it2, src); }, 5);
+    const double nf = (double)128 * 32 * 16 * it2 * sms * 4;
     CK(cudaDeviceSynchronize());
     int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"sm_clock_max_mhz\": %.0f, "
            "\"dfma_tflops\": %.3f, \"dmul_tops\": %.3f, "
+           "\"dfma_rm_tflops\": %.3f, \"filter_relax_per_s_2cta\": %.4e, \"filter_relax_per_s_3cta\": %.4e, \"filter_relax_per_s_4cta\": %.4e, "
            "\"relax_per_s\": %.4e, \"relax_val_only_per_s\": %.4e, "
            "\"nominal_fp64_fma_tflops\": %.2f, \"nominal_relax_ceiling_per_s\": %.4e}\n",
            p.name, sms, clk / 1000.0, 2.0 * n1 / (t_dfma * 1e-3) / 1e12, n1 / (t_dmul * 1e-3) / 1e12,
+           2.0 * n1 / (t_dfma_rm * 1e-3) / 1e12, nf * 2 / (t_f2 * 1e-3), nf * 3 / (t_f3 * 1e-3), nf * 4 / (t_f4 * 1e-3),
            n2 / (t_rel * 1e-3), n2 / (t_relv * 1e-3), sms * 64 * 2 * (clk / 1e6) / 1e3 ,
            sms * 32.0 * clk * 1e3);
     return 0;

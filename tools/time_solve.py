@@ -22,7 +22,11 @@ for n in sizes:
         e0.record(); dense.solve_device(ctx, r, x); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     ms, cnt = ctx.phase_ms()
+    spans = ctx.phase_spans(3)
     ctx.set_profiling(False)
+    if spans:
+        q = max(1, len(spans) // 8)
+        print("  bulk ms per launch (every %d-th): " % q + " ".join(f"{v:.3f}" for v in spans[::q]))
     print(json.dumps({"n": n, "ms": round(best, 3), "relax_per_s": f"{n**3 / (best * 1e-3):.4e}",
                       "phase_ms": [round(m, 3) for m in ms], "phase_launches": cnt,
                       "bulk_relax_per_s": f"{(n - 128) ** 2 * 128 * cnt[3] / (ms[3] * 1e-3 + 1e-12):.4e}"}))
