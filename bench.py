@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--n", type=int, default=0, help="override the matrix order (debug only)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--check", action="store_true",
+                    help="multi-GPU: verify the sharded result against a single-GPU solve (small --n only)")
     return ap.parse_args()
 
 

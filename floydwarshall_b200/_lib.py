@@ -27,6 +27,7 @@ SYMBOLS = (
     "fw_ctx_set_stream", "fw_ctx_last_launches", "fw_solve", "fw_solve_device", "fw_solve_batched",
     "fw_solve_batched_device", "fw_ctx_synchronize", "fw_ctx_set_profiling", "fw_ctx_phase_ms",
     "fw_ctx_phase_spans", "fw_shard_validate", "fw_shard_pivot", "fw_shard_update",
+    "fw_paths", "fw_paths_device",
 )
 
 
@@ -75,6 +76,10 @@ def load():
     L.fw_shard_pivot.argtypes = [vp, i32, i32, i32, i64, vp, vp, i32, vp]
     L.fw_shard_update.restype = ctypes.c_int
     L.fw_shard_update.argtypes = [vp, i32, i32, i32, i64, vp, vp, i32, vp]
+    L.fw_paths.restype = ctypes.c_int
+    L.fw_paths.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i64]
+    L.fw_paths_device.restype = ctypes.c_int
+    L.fw_paths_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, i64]
     L.fw_solve.restype = ctypes.c_int
     L.fw_solve.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.fw_solve_device.restype = ctypes.c_int

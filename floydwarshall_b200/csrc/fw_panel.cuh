@@ -32,7 +32,8 @@ struct PanelArgs {
     int b0;         // first pivot of the k-block (global index)
     int rows;       // rows held by this shard (== npad when unsharded)
     int blk_r0;     // LOCAL row of pivot b0 if this shard holds the k-block rows, else INT_MAX
-    double *Cp;     // N x B column snapshots
+    double *Cp;     // B x rows column snapshots, TRANSPOSED: Cp[kk*ldc + i]
+    long long ldc;
     int32_t *NCp;
     double *Rw;     // B x N row snapshots
     long long ldw;
@@ -112,9 +113,8 @@ __global__ void __launch_bounds__(512, 1) fw_colpanel_kernel(PanelArgs a) {
             pn[0] = make_int4(nx[0], nx[1], nx[2], nx[3]);
             pn[1] = make_int4(nx[4], nx[5], nx[6], nx[7]);
             const long long poff = (long long)i * FW_B + l * 8;
-            double2 *pc = reinterpret_cast<double2 *>(a.Cp + poff);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) pc[q] = make_double2(cs[q * 2], cs[q * 2 + 1]);
+            for (int c = 0; c < 8; ++c) a.Cp[(long long)(l * 8 + c) * a.ldc + i] = cs[c];
             int4 *pnc = reinterpret_cast<int4 *>(a.NCp + poff);
             pnc[0] = make_int4(ncs[0], ncs[1], ncs[2], ncs[3]);
             pnc[1] = make_int4(ncs[4], ncs[5], ncs[6], ncs[7]);
@@ -136,10 +136,10 @@ __global__ void __launch_bounds__(512, 1) fw_rowpanel_kernel(PanelArgs a) {
     double *Fs = reinterpret_cast<double *>(smem_raw);
     const int tid = threadIdx.x;
     const int b0 = a.b0;
-    // factor matrix F[kk][i] = Cd[i][kk] = Cp[(blk_r0+i)*B + kk]   (transposed fill; owner shard only)
+    // factor matrix F[kk][i] = Cd[i][kk] = Cp[kk*ldc + blk_r0 + i]   (owner shard only)
     for (int idx = tid; idx < 128 * 128; idx += 512) {
-        const int i = idx >> 7, kk = idx & 127;
-        Fs[kk * PANEL_FP + swz128(i)] = a.Cp[(long long)(a.blk_r0 + i) * FW_B + kk];
+        const int kk = idx >> 7, i = idx & 127;
+        Fs[kk * PANEL_FP + swz128(i)] = a.Cp[(long long)kk * a.ldc + a.blk_r0 + i];
     }
     __syncthreads();
 

@@ -3,7 +3,7 @@
 // Two uses:
 //  * phase 1 of the blocked solve: the pivot diagonal tile of k-block b0, which
 //    additionally emits the step-k snapshots the other phases consume
-//      Cp [(b0+i)*B + kk] = R[i][b0+kk]  as of step b0+kk   (column snapshot)
+//      Cp [kk*ldc + i]    = R[i][b0+kk]  as of step b0+kk   (column snapshot, transposed)
 //      NCp[(b0+i)*B + kk] = NX[i][b0+kk] as of step b0+kk
 //      Rw [kk*ldw + b0+j] = R[b0+kk][j]  as of step b0+kk   (row snapshot)
 //    (the reference reads row k / column k AS OF STEP k, so the
@@ -34,7 +34,8 @@ struct TileArgs {
     int b0;                 // tile origin: global column (== global row of the pivots)
     int r0;                 // tile origin: LOCAL row inside this shard (== b0 when unsharded)
     int nv;                 // valid rows/cols inside the tile (1..128)
-    double *Cp;             // snapshot outputs; null in batched mode
+    double *Cp;             // snapshot outputs; null in batched mode.  Cp is TRANSPOSED: Cp[kk*ldc + row]
+    long long ldc;
     int32_t *NCp;
     double *Rw;
     long long ldw;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(512, 1) fw_tile_kernel(TileArgs a) {
                 // snapshots for the other phases (diag mode only)
                 if (a.Cp != nullptr) {
                     if (tid < 128) {
-                        a.Cp[(long long)(a.r0 + tid) * FW_B + k] = cb[tid];
+                        a.Cp[(long long)k * a.ldc + a.r0 + tid] = cb[tid];
                         a.NCp[(long long)(a.r0 + tid) * FW_B + k] = NXs[tid * TILE_NXP + k];
                     } else if (tid < 256) {
                         const int j = tid - 128;

@@ -17,12 +17,14 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <numeric>
 #include <vector>
 
 #include "../../include/fwgpu.h"
 #include "fw_bulk.cuh"
 #include "fw_common.cuh"
 #include "fw_panel.cuh"
+#include "fw_paths.cuh"
 #include "fw_tile.cuh"
 
 static_assert(FW_B == FW_TILE, "kernel block size and public tile size must agree");
@@ -127,7 +129,7 @@ struct fw_ctx {
     int *d_flag = nullptr;
     int *h_flag = nullptr;
     bool attrs_set = false;
-    int bulk_window = 1;   // k steps filtered per warp vote in fw_bulk_kernel (experiment knob: FW_BULK_WINDOW)
+    int bulk_cq = 2;       // fw_bulk_kernel tile width / 32 (2: 8x4 micro-tile, 4: 8x8); knob FW_BULK_CQ
     // optional per-phase timing (CUDA events on the launching stream)
     bool profiling = false;
     struct Span { cudaEvent_t a, b; int phase; };
@@ -151,13 +153,13 @@ int set_kernel_attrs(fw_ctx *c) {
                             (int)fw::panel_smem_bytes()));
     CU(cudaFuncSetAttribute(fw::fw_rowpanel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)fw::panel_smem_bytes()));
-    CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)fw::bulk_smem_bytes()));
-    CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)fw::bulk_smem_bytes()));
+                            (int)fw::bulk_smem_bytes<2>()));
     CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    if (const char *e = getenv("FW_BULK_WINDOW")) c->bulk_window = atoi(e) == 2 ? 2 : 1;
+    CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::bulk_smem_bytes<4>()));
+    CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    if (const char *e = getenv("FW_BULK_CQ")) c->bulk_cq = atoi(e) == 4 ? 4 : 2;
     c->attrs_set = true;
     return FW_OK;
 }
@@ -191,6 +193,17 @@ int grid_for(long long total, int sm_count) {
     return (int)g;
 }
 
+void launch_bulk(fw_ctx *c, const fw::BulkArgs &g, int ncols, int rows_out) {
+    PhaseTimer pt(c, 3);
+    if (c->bulk_cq == 4) {
+        const dim3 grid(ncols / 128 - 1, rows_out / fw::BULK_TR);
+        fw::fw_bulk_kernel<4><<<grid, 128, fw::bulk_smem_bytes<4>(), c->stream>>>(g);
+    } else {
+        const dim3 grid(ncols / 64 - 2, rows_out / fw::BULK_TR);
+        fw::fw_bulk_kernel<2><<<grid, 128, fw::bulk_smem_bytes<2>(), c->stream>>>(g);
+    }
+}
+
 // Domain check (synchronises the stream once).
 int validate_device(fw_ctx *c, const double *rate, const int32_t *next, long long ld, long long stride,
                     int batch, int n, int rows = -1, int row0 = 0) {
@@ -219,13 +232,12 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
     const int nblk = npad / FW_B;
     const int njobs32 = (npad - FW_B) / 32;
     const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
-    const int nt = npad / fw::BULK_T - FW_B / fw::BULK_T;
     for (int b = 0; b < nblk; ++b) {
         const int b0 = b * FW_B;
         fw::TileArgs t;
         t.rate = rate; t.next = next; t.mid = mid; t.csT = csT; t.rs = rs;
         t.ld = ld; t.batch_stride = 0; t.b0 = b0; t.r0 = b0; t.nv = FW_B;
-        t.Cp = c->Cp.p; t.NCp = c->NCp.p; t.Rw = c->Rw.p; t.ldw = npad;
+        t.Cp = c->Cp.p; t.ldc = npad; t.NCp = c->NCp.p; t.Rw = c->Rw.p; t.ldw = npad;
         {
             PhaseTimer pt(c, 0);
             if (paths)
@@ -238,7 +250,7 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
             fw::PanelArgs p;
             p.rate = rate; p.next = next; p.mid = mid; p.csT = csT; p.rs = rs;
             p.ld = ld; p.npad = npad; p.b0 = b0; p.rows = npad; p.blk_r0 = b0;
-            p.Cp = c->Cp.p; p.NCp = c->NCp.p; p.Rw = c->Rw.p; p.ldw = npad;
+            p.Cp = c->Cp.p; p.ldc = npad; p.NCp = c->NCp.p; p.Rw = c->Rw.p; p.ldw = npad;
             {
                 PhaseTimer pt(c, 1);
                 if (paths) fw::fw_colpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
@@ -253,14 +265,8 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
             fw::BulkArgs g;
             g.rate = rate; g.next = next; g.mid = mid; g.ld = ld; g.npad = npad; g.b0 = b0;
             g.rows = npad; g.row0 = 0; g.blk_r0 = b0;
-            g.Cp = c->Cp.p; g.NCp = c->NCp.p; g.Rw = c->Rw.p; g.ldw = npad;
-            {
-                PhaseTimer pt(c, 3);
-                if (c->bulk_window == 2)
-                    fw::fw_bulk_kernel<2><<<dim3(nt, nt), 128, fw::bulk_smem_bytes(), c->stream>>>(g);
-                else
-                    fw::fw_bulk_kernel<1><<<dim3(nt, nt), 128, fw::bulk_smem_bytes(), c->stream>>>(g);
-            }
+            g.CpT = c->Cp.p; g.ldc = npad; g.NCp = c->NCp.p; g.Rw = c->Rw.p; g.ldw = npad;
+            launch_bulk(c, g, npad, npad - FW_B);
             c->launches++;
         }
         CU(cudaGetLastError());
@@ -280,7 +286,7 @@ int solve_tiles(fw_ctx *c, int batch, int n, long long ld, long long stride, dou
     fw::TileArgs t;
     t.rate = rate; t.next = next; t.mid = mid; t.csT = csT; t.rs = rs;
     t.ld = ld; t.batch_stride = stride; t.b0 = 0; t.r0 = 0; t.nv = n;
-    t.Cp = nullptr; t.NCp = nullptr; t.Rw = nullptr; t.ldw = 0;
+    t.Cp = nullptr; t.ldc = 0; t.NCp = nullptr; t.Rw = nullptr; t.ldw = 0;
     {
         PhaseTimer pt(c, 0);
         if (paths)
@@ -625,6 +631,88 @@ int fw_solve_batched(fw_ctx *c, int32_t batch, int32_t n, double *rate, int32_t 
     return FW_OK;
 }
 
+/* ---- exact `_path` expansion (Algorithms.hs:55) --------------------------- */
+int fw_paths_device(fw_ctx *c, int32_t n, int64_t ld, const int32_t *d_init_next, const int32_t *d_mid,
+                    const int32_t *d_csT, const int32_t *d_rs, int32_t nq, const int32_t *queries,
+                    int64_t *offsets, int32_t *verts, int64_t cap) {
+    if (n < 0 || nq < 0 || !offsets) return fail(FW_ERR_INVALID, "fw_paths: bad argument");
+    offsets[0] = 0;
+    if (nq == 0 || n == 0) { for (int i = 0; i < nq; ++i) offsets[i + 1] = 0; return FW_OK; }
+    if (!d_init_next || !d_mid || !d_csT || !d_rs || !queries || ld < n)
+        return fail(FW_ERR_INVALID, "fw_paths: null table");
+    int rc = get_ctx(c, &c);
+    if (rc != FW_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    int32_t *d_q = nullptr; long long *d_len = nullptr, *d_off = nullptr; int32_t *d_verts = nullptr;
+    auto cleanup = [&]() { cudaFree(d_q); cudaFree(d_len); cudaFree(d_off); cudaFree(d_verts); };
+    std::vector<long long> h_len(nq), h_off((size_t)nq + 1);
+    cudaError_t e;
+    if ((e = cudaMalloc(&d_q, sizeof(int32_t) * 2 * (size_t)nq)) != cudaSuccess ||
+        (e = cudaMalloc(&d_len, sizeof(long long) * (size_t)nq)) != cudaSuccess ||
+        (e = cudaMalloc(&d_off, sizeof(long long) * ((size_t)nq + 1))) != cudaSuccess) {
+        cleanup(); return cuda_fail(e, "cudaMalloc");
+    }
+    fw::PathArgs a;
+    a.init_next = d_init_next; a.mid = d_mid; a.csT = d_csT; a.rs = d_rs; a.ld = ld; a.n = n; a.nq = nq;
+    a.queries = d_q; a.lengths = d_len; a.offsets = d_off; a.verts = nullptr;
+    a.max_len = (cap > 0) ? cap : 0x7fffffffffffLL; a.flag = c->d_flag;
+    const int grid = (nq + 63) / 64;
+    if ((e = cudaMemcpyAsync(d_q, queries, sizeof(int32_t) * 2 * (size_t)nq, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+        (e = cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream)) != cudaSuccess) { cleanup(); return cuda_fail(e, "copy"); }
+    fw::fw_paths_kernel<0><<<grid, 64, 0, c->stream>>>(a);
+    c->launches++;
+    if ((e = cudaMemcpyAsync(h_len.data(), d_len, sizeof(long long) * (size_t)nq, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { cleanup(); return cuda_fail(e, "fw_paths pass 0"); }
+    if (*c->h_flag & 4) { cleanup(); return fail(FW_ERR_INVALID, "fw_paths: query vertex out of range"); }
+    if (*c->h_flag & 1) { cleanup(); return fail(FW_ERR_CAP, "fw_paths: path recursion deeper than the device stack"); }
+    h_off[0] = 0;
+    for (int i = 0; i < nq; ++i) h_off[i + 1] = h_off[i] + h_len[i];
+    for (int i = 0; i <= nq; ++i) offsets[i] = h_off[i];
+    if ((*c->h_flag & 2) || h_off[nq] > cap) {
+        cleanup();
+        return fail(FW_ERR_CAP, "fw_paths: output capacity too small (offsets hold the lengths found so far)");
+    }
+    if (h_off[nq] > 0) {
+        if (!verts) { cleanup(); return fail(FW_ERR_INVALID, "fw_paths: verts is null"); }
+        if ((e = cudaMalloc(&d_verts, sizeof(int32_t) * (size_t)h_off[nq])) != cudaSuccess) { cleanup(); return cuda_fail(e, "cudaMalloc"); }
+        a.verts = d_verts;
+        if ((e = cudaMemcpyAsync(d_off, h_off.data(), sizeof(long long) * ((size_t)nq + 1), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) { cleanup(); return cuda_fail(e, "copy"); }
+        fw::fw_paths_kernel<1><<<grid, 64, 0, c->stream>>>(a);
+        c->launches++;
+        if ((e = cudaMemcpyAsync(verts, d_verts, sizeof(int32_t) * (size_t)h_off[nq], cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { cleanup(); return cuda_fail(e, "fw_paths pass 1"); }
+    }
+    cleanup();
+    return FW_OK;
+}
+
+int fw_paths(fw_ctx *c, int32_t n, const int32_t *init_next, const int32_t *mid, const int32_t *csT,
+             const int32_t *rs, int32_t nq, const int32_t *queries, int64_t *offsets, int32_t *verts,
+             int64_t cap) {
+    if (n < 0 || nq < 0 || !offsets) return fail(FW_ERR_INVALID, "fw_paths: bad argument");
+    if (n == 0 || nq == 0) return fw_paths_device(c, n, n, nullptr, nullptr, nullptr, nullptr, nq, queries, offsets, verts, cap);
+    if (!init_next || !mid || !csT || !rs) return fail(FW_ERR_INVALID, "fw_paths: null table");
+    int rc = get_ctx(c, &c);
+    if (rc != FW_OK) return rc;
+    const size_t tot = (size_t)n * n;
+    int32_t *d[4] = {nullptr, nullptr, nullptr, nullptr};
+    const int32_t *h[4] = {init_next, mid, csT, rs};
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        CU(cudaSetDevice(c->device));
+        for (int i = 0; i < 4; ++i) {
+            cudaError_t e = cudaMalloc(&d[i], tot * 4);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(d[i], h[i], tot * 4, cudaMemcpyHostToDevice, c->stream);
+            if (e != cudaSuccess) { for (int j = 0; j < 4; ++j) cudaFree(d[j]); return cuda_fail(e, "fw_paths upload"); }
+        }
+    }
+    rc = fw_paths_device(c, n, n, d[0], d[1], d[2], d[3], nq, queries, offsets, verts, cap);
+    for (int j = 0; j < 4; ++j) cudaFree(d[j]);
+    return rc;
+}
+
 /* ---- row-sharded building blocks (multi-GPU) ------------------------------- */
 static int shard_args_ok(int32_t n, int32_t row0, int32_t rows, int64_t ld, const void *rate, const void *next,
                          int32_t b0, const void *Rw) {
@@ -661,7 +749,7 @@ int fw_shard_pivot(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld,
     fw::TileArgs t;
     t.rate = d_rate; t.next = d_next; t.mid = nullptr; t.csT = nullptr; t.rs = nullptr;
     t.ld = ld; t.batch_stride = 0; t.b0 = b0; t.r0 = blk_r0; t.nv = FW_B;
-    t.Cp = c->Cp.p; t.NCp = c->NCp.p; t.Rw = d_Rw; t.ldw = n;
+    t.Cp = c->Cp.p; t.ldc = rows; t.NCp = c->NCp.p; t.Rw = d_Rw; t.ldw = n;
     {
         PhaseTimer pt(c, 0);
         fw::fw_tile_kernel<false><<<1, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
@@ -671,7 +759,7 @@ int fw_shard_pivot(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld,
         fw::PanelArgs p;
         p.rate = d_rate; p.next = d_next; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
         p.ld = ld; p.npad = n; p.b0 = b0; p.rows = rows; p.blk_r0 = blk_r0;
-        p.Cp = c->Cp.p; p.NCp = c->NCp.p; p.Rw = d_Rw; p.ldw = n;
+        p.Cp = c->Cp.p; p.ldc = rows; p.NCp = c->NCp.p; p.Rw = d_Rw; p.ldw = n;
         const int njobs32 = (n - FW_B) / 32;
         const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
         PhaseTimer pt(c, 2);
@@ -700,7 +788,7 @@ int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld
         fw::PanelArgs p;
         p.rate = d_rate; p.next = d_next; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
         p.ld = ld; p.npad = n; p.b0 = b0; p.rows = rows; p.blk_r0 = blk_r0;
-        p.Cp = c->Cp.p; p.NCp = c->NCp.p; p.Rw = const_cast<double *>(d_Rw); p.ldw = n;
+        p.Cp = c->Cp.p; p.ldc = rows; p.NCp = c->NCp.p; p.Rw = const_cast<double *>(d_Rw); p.ldw = n;
         const int njobs32 = rows_out / 32;
         const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
         {
@@ -711,15 +799,8 @@ int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld
         fw::BulkArgs g;
         g.rate = d_rate; g.next = d_next; g.mid = nullptr; g.ld = ld; g.npad = n; g.b0 = b0;
         g.rows = rows; g.row0 = row0; g.blk_r0 = blk_r0;
-        g.Cp = c->Cp.p; g.NCp = c->NCp.p; g.Rw = d_Rw; g.ldw = n;
-        const dim3 grid(n / fw::BULK_T - FW_B / fw::BULK_T, rows_out / fw::BULK_T);
-        {
-            PhaseTimer pt(c, 3);
-            if (c->bulk_window == 2)
-                fw::fw_bulk_kernel<2><<<grid, 128, fw::bulk_smem_bytes(), c->stream>>>(g);
-            else
-                fw::fw_bulk_kernel<1><<<grid, 128, fw::bulk_smem_bytes(), c->stream>>>(g);
-        }
+        g.CpT = c->Cp.p; g.ldc = rows; g.NCp = c->NCp.p; g.Rw = d_Rw; g.ldw = n;
+        launch_bulk(c, g, n, rows_out);
         c->launches++;
     }
     CU(cudaGetLastError());

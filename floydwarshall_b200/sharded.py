@@ -185,6 +185,32 @@ def bench_main(args, METRIC, UNIT, SEED, workload_n, workload_name, ClockSampler
     launches = torch.tensor([be.launches], dtype=torch.int64, device=dev)
     dist.all_reduce(launches)
 
+    check = None
+    if getattr(args, "check", False):
+        from . import dense
+        full_r = [torch.empty_like(r) for _ in range(world)]
+        full_x = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(full_r, r)
+        dist.all_gather(full_x, x)
+        if rank == 0:
+            R0 = [torch.empty_like(r0) for _ in range(world)]
+        p_r = [torch.empty_like(r0) for _ in range(world)]
+        p_x = [torch.empty_like(x0) for _ in range(world)]
+        dist.all_gather(p_r, r0)
+        dist.all_gather(p_x, x0)
+        if rank == 0:
+            fr, fx = torch.cat(p_r).contiguous(), torch.cat(p_x).contiguous()
+            c2 = _lib.Context(local)
+            c2.set_stream(torch.cuda.current_stream().cuda_stream)
+            dense.solve_device(c2, fr, fx)
+            torch.cuda.synchronize()
+            same = bool(torch.equal(fr.view(torch.int64), torch.cat(full_r).view(torch.int64))) and \
+                bool(torch.equal(fx, torch.cat(full_x)))
+            c2.close()
+            if not same:
+                raise SystemExit("sharded result differs from the single-GPU solve")
+            check = "bit-exact vs single-GPU fw_solve_device"
+
     # per-phase profile of one step on this rank (bulk kernel roofline)
     ctx.set_profiling(True)
     r.copy_(r0); x.copy_(x0)
@@ -232,7 +258,8 @@ def bench_main(args, METRIC, UNIT, SEED, workload_n, workload_name, ClockSampler
             "config": {"workload": workload_name(n), "n": n, "seed": SEED + 1, "k_block": B,
                        "sharding": f"row blocks of {rows} rows per rank; per-k-block NCCL broadcast of the "
                                    f"128 x {n} fp64 pivot-row snapshot panel ({B * n * 8 / 2**20:.0f} MiB)",
-                       "l2": "per-rank inputs are far larger than the 126 MB L2; no flush needed"},
+                       "l2": "per-rank inputs are far larger than the 126 MB L2; no flush needed",
+                       "check": check},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()),
             "roofline": {"bound": "fp64", "kernel": "fw_bulk_kernel", "achieved": ach, "peak": peak_tflops,
                          "unit": "TFLOP/s", "frac": (ach / peak_tflops) if ach else None, "traffic": None,

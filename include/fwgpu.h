@@ -110,6 +110,23 @@ int fw_solve_batched_device(fw_ctx *ctx, int32_t batch, int32_t n,
                             double *d_rate, int32_t *d_next, int32_t *d_mid,
                             int32_t *d_csT, int32_t *d_rs);
 
+/* ---- replaces the `_path` field of RateEntry (Algorithms.hs:55) ------------
+ * Expands, on the device, the exact reference path (start excluded, destination
+ * included) of nq (src,dst) index pairs from the side tables of a paths-enabled
+ * solve plus the PRE-solve next matrix (`edge(a,b)` exists iff
+ * init_next[a*n+b] >= 0).  offsets[nq+1] and verts[cap] are host outputs in CSR
+ * form.  If the paths need more than `cap` entries the call returns FW_ERR_CAP
+ * with offsets filled from the lengths found (so the caller can re-size).
+ * Unreachable pairs yield empty paths.  fw_paths takes HOST tables (n x n),
+ * fw_paths_device DEVICE tables with leading dimension ld. */
+int fw_paths(fw_ctx *ctx, int32_t n, const int32_t *init_next, const int32_t *mid,
+             const int32_t *csT, const int32_t *rs, int32_t nq, const int32_t *queries,
+             int64_t *offsets, int32_t *verts, int64_t cap);
+int fw_paths_device(fw_ctx *ctx, int32_t n, int64_t ld, const int32_t *d_init_next,
+                    const int32_t *d_mid, const int32_t *d_csT, const int32_t *d_rs,
+                    int32_t nq, const int32_t *queries, int64_t *offsets, int32_t *verts,
+                    int64_t cap);
+
 /* ---- row-sharded building blocks (one shard per GPU) ----------------------
  * The multi-GPU solve keeps rows [row0, row0+rows) of the n x n
  * matrix on each GPU (n, row0, rows multiples of FW_TILE; ld % 4 == 0).  For

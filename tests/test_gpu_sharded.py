@@ -1,0 +1,73 @@
+"""Row-sharded entry points (fw_shard_*) on ONE GPU: the P shards of a matrix are driven in
+sequence through the same schedule the multi-GPU path uses (the Rw panel is copied between
+the shard backends instead of NCCL-broadcast), and the gathered result must equal the CPU
+oracle bit for bit.  (No inter-waiting kernels: everything is stream-ordered on one device.)"""
+import numpy as np
+import pytest
+
+from floydwarshall_b200 import _lib, graphs, sharded
+from oracle import fw_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("world,E,C,mode", [(1, 24, 16, "consistent"), (2, 32, 16, "consistent"),
+                                            (4, 32, 16, "arbitrage"), (2, 16, 16, "pow2")])
+def test_virtual_ranks_on_one_gpu(world, E, C, mode):
+    import torch
+    n = E * C
+    rate, nxt = graphs.exchange_graph(E, C, seed=31, density=0.7, mode=mode)
+    ref = O.solve_dense(rate, nxt, threads=0)
+    rows = sharded.shard_rows(n, world)
+    ctxs = [_lib.Context(0) for _ in range(world)]
+    stream = torch.cuda.current_stream().cuda_stream
+    bes = []
+    for r in range(world):
+        ctxs[r].set_stream(stream)
+        rt = torch.from_numpy(rate[r * rows:(r + 1) * rows].copy()).cuda()
+        xt = torch.from_numpy(nxt[r * rows:(r + 1) * rows].copy()).cuda()
+        be = sharded.GpuShardBackend(ctxs[r], n, r * rows, rt, xt)
+        be.validate()
+        bes.append(be)
+    for b0 in range(0, n, sharded.B):
+        owner = b0 // rows
+        bes[owner].pivot(b0)
+        for r in range(world):
+            if r != owner:
+                bes[r].Rw.copy_(bes[owner].Rw)      # stands in for dist.broadcast(Rw, src=owner)
+        for r in range(world):
+            bes[r].update(b0)
+    torch.cuda.synchronize()
+    got_r = np.concatenate([be.rate.cpu().numpy() for be in bes])
+    got_x = np.concatenate([be.next.cpu().numpy() for be in bes])
+    assert np.array_equal(got_r.view(np.uint64), ref.rate.view(np.uint64))
+    assert np.array_equal(got_x, ref.next)
+    for c in ctxs:
+        c.close()
+
+
+def test_device_graph_shard_matches_host_generator():
+    import torch
+    n, ccy = 512, 16
+    rate, nxt = graphs.exchange_graph(n // ccy, ccy, seed=77)
+    for row0, rows in ((0, 512), (128, 256), (384, 128)):
+        r, x = sharded.device_graph_shard(n, ccy, 77, row0, rows, torch.device("cuda", 0))
+        assert np.array_equal(r.cpu().numpy(), rate[row0:row0 + rows])
+        assert np.array_equal(x.cpu().numpy(), nxt[row0:row0 + rows])
+
+
+def test_two_process_nccl_if_two_gpus(tmp_path):
+    """Real 2-rank NCCL run when the box has >= 2 GPUs (skipped otherwise)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import subprocess, sys, os, json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29611",
+                          os.path.join(root, "bench.py"), "--gpus", "2", "--steps", "1", "--warmup", "1",
+                          "--n", "2048", "--skip-e2e", "--check"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["n_gpus"] == 2 and d["config"].get("check") == "bit-exact vs single-GPU fw_solve_device"
