@@ -172,6 +172,7 @@ def run_reference(args):
     threads = O.max_threads()
     rate, nxt = host_graph(n, SEED)
     ksteps = max(1, int(8 * (32768 / n) ** 2))          # ~8.6e9 relaxations per step
+    ksteps = min(ksteps, max(1, n // (args.warmup + args.steps)))   # stay inside the n pivots
     t_steps = []
     k = 0
     for s in range(args.warmup + args.steps):

@@ -656,7 +656,8 @@ int fw_paths_device(fw_ctx *c, int32_t n, int64_t ld, const int32_t *d_init_next
     fw::PathArgs a;
     a.init_next = d_init_next; a.mid = d_mid; a.csT = d_csT; a.rs = d_rs; a.ld = ld; a.n = n; a.nq = nq;
     a.queries = d_q; a.lengths = d_len; a.offsets = d_off; a.verts = nullptr;
-    a.max_len = (cap > 0) ? cap : 0x7fffffffffffLL; a.flag = c->d_flag;
+    a.max_len = 1LL << 24;   // hard per-path bound (arbitrage cycles make paths grow exponentially)
+    a.flag = c->d_flag;
     const int grid = (nq + 63) / 64;
     if ((e = cudaMemcpyAsync(d_q, queries, sizeof(int32_t) * 2 * (size_t)nq, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
         (e = cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream)) != cudaSuccess) { cleanup(); return cuda_fail(e, "copy"); }
@@ -670,9 +671,10 @@ int fw_paths_device(fw_ctx *c, int32_t n, int64_t ld, const int32_t *d_init_next
     h_off[0] = 0;
     for (int i = 0; i < nq; ++i) h_off[i + 1] = h_off[i] + h_len[i];
     for (int i = 0; i <= nq; ++i) offsets[i] = h_off[i];
-    if ((*c->h_flag & 2) || h_off[nq] > cap) {
+    if (*c->h_flag & 2) { cleanup(); return fail(FW_ERR_CAP, "fw_paths: a path is longer than 2^24 hops"); }
+    if (h_off[nq] > cap) {
         cleanup();
-        return fail(FW_ERR_CAP, "fw_paths: output capacity too small (offsets hold the lengths found so far)");
+        return fail(FW_ERR_CAP, "fw_paths: output capacity too small (offsets[nq] holds the size needed)");
     }
     if (h_off[nq] > 0) {
         if (!verts) { cleanup(); return fail(FW_ERR_INVALID, "fw_paths: verts is null"); }

@@ -192,8 +192,6 @@ def bench_main(args, METRIC, UNIT, SEED, workload_n, workload_name, ClockSampler
         full_x = [torch.empty_like(x) for _ in range(world)]
         dist.all_gather(full_r, r)
         dist.all_gather(full_x, x)
-        if rank == 0:
-            R0 = [torch.empty_like(r0) for _ in range(world)]
         p_r = [torch.empty_like(r0) for _ in range(world)]
         p_x = [torch.empty_like(x0) for _ in range(world)]
         dist.all_gather(p_r, r0)

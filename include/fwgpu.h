@@ -116,7 +116,8 @@ int fw_solve_batched_device(fw_ctx *ctx, int32_t batch, int32_t n,
  * solve plus the PRE-solve next matrix (`edge(a,b)` exists iff
  * init_next[a*n+b] >= 0).  offsets[nq+1] and verts[cap] are host outputs in CSR
  * form.  If the paths need more than `cap` entries the call returns FW_ERR_CAP
- * with offsets filled from the lengths found (so the caller can re-size).
+ * with offsets filled (offsets[nq] = entries needed) so the caller can re-size.
+ * A single path longer than 2^24 hops (arbitrage cycles) is FW_ERR_CAP too.
  * Unreachable pairs yield empty paths.  fw_paths takes HOST tables (n x n),
  * fw_paths_device DEVICE tables with leading dimension ld. */
 int fw_paths(fw_ctx *ctx, int32_t n, const int32_t *init_next, const int32_t *mid,
