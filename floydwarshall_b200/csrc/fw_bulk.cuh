@@ -48,9 +48,10 @@ struct BulkArgs {
 
 constexpr int BULK_TR = 64;   // tile rows
 constexpr int BULK_KC = 16;   // k-chunk
+constexpr int BULK_ST = 3;    // cp.async pipeline stages (one __syncthreads per chunk)
 template <int CQ>
 constexpr size_t bulk_smem_bytes() {
-    return sizeof(double) * 2 * BULK_KC * (BULK_TR + 32 * CQ) + sizeof(int) * (16 * CQ) * 128;
+    return sizeof(double) * BULK_ST * BULK_KC * (BULK_TR + 32 * CQ) + sizeof(int) * (16 * CQ) * 128;
 }
 
 template <int N>
@@ -69,11 +70,11 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
     typedef double (*AsT)[BULK_KC][BULK_TR];
     typedef double (*BsT)[BULK_KC][TW];
     typedef int (*MsT)[128];
-    AsT As = reinterpret_cast<AsT>(bulk_smem);                                               // [2][16][64]
-    BsT Bs = reinterpret_cast<BsT>(bulk_smem + sizeof(double) * 2 * BULK_KC * BULK_TR);      // [2][16][TW]
+    AsT As = reinterpret_cast<AsT>(bulk_smem);                                                    // [ST][16][64]
+    BsT Bs = reinterpret_cast<BsT>(bulk_smem + sizeof(double) * BULK_ST * BULK_KC * BULK_TR);     // [ST][16][TW]
     // mid (k of the last replacement) per entry: written only on the rare exact path, so it lives in
     // shared memory ([entry][thread], conflict-free) and leaves the registers to the DFMA results.
-    MsT Ms = reinterpret_cast<MsT>(bulk_smem + sizeof(double) * 2 * BULK_KC * (BULK_TR + TW)); // [8*NC][128]
+    MsT Ms = reinterpret_cast<MsT>(bulk_smem + sizeof(double) * BULK_ST * BULK_KC * (BULK_TR + TW)); // [8*NC][128]
 
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
@@ -103,6 +104,8 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
 
     load_chunk(0, 0);
     cp_async_commit();
+    load_chunk(1, 1);
+    cp_async_commit();
 
     double o[8][NC];
     unsigned long long chg = 0;   // bit e set <=> entry e of this thread was replaced (Ms[e][tid] valid)
@@ -130,16 +133,15 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
     }
 
     constexpr int NCH = FW_B / BULK_KC;
+    int buf = 0;
     for (int ch = 0; ch < NCH; ++ch) {
-        const int buf = ch & 1;
-        if (ch + 1 < NCH) {
-            load_chunk(ch + 1, buf ^ 1);
+        // chunk ch has landed once at most one younger group is still in flight
+        if (ch + 1 < NCH) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();   // (a) chunk ch visible to all; (b) everyone is done with chunk ch-1's buffer
+        if (ch + 2 < NCH) {
+            load_chunk(ch + 2, (buf + 2) % BULK_ST);   // == the buffer chunk ch-1 used
             cp_async_commit();
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
         }
-        __syncthreads();
         // operands of step kk are fetched one step ahead so that their shared-memory latency
         // hides behind the previous step's DFMAs and vote
         double av[8], bv[NC];
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
             }
         };
         fetch(0, av, bv);
-#pragma unroll 4
+#pragma unroll 2
         for (int kk = 0; kk < BULK_KC; ++kk) {
             double avn[8], bvn[NC];
             fetch((kk + 1 < BULK_KC) ? kk + 1 : kk, avn, bvn);
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
 #pragma unroll
             for (int c = 0; c < NC; ++c) bv[c] = bvn[c];
         }
-        __syncthreads();
+        buf = (buf + 1) % BULK_ST;
     }
 
     // ---- epilogue: only entries that were replaced are written back ----
