@@ -86,25 +86,31 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
     const int i0 = ti * BULK_TR, j0 = tj * TW;
     const long long ld = a.ld;
 
-    auto load_chunk = [&](int ch, int buf) {
-        const int kk0 = ch * BULK_KC;
+    // cp.async sources/destinations of this thread, computed once: piece p = tid + 128*t covers
+    // A: row kk = (tid>>5) + 4t, 16 bytes at column (tid&31)*2;  B: likewise with TW/2 pieces per row.
+    const double *srcA = a.CpT + (long long)(tid >> 5) * a.ldc + i0 + (tid & 31) * 2;
+    const double *srcB = a.Rw + (long long)(tid / (TW / 2)) * a.ldw + j0 + (tid % (TW / 2)) * 2;
+    const long long stepA = 4 * a.ldc;                      // +4 rows per t
+    const long long stepB = (long long)(128 / (TW / 2)) * a.ldw;
+    const unsigned dstA = (unsigned)__cvta_generic_to_shared(&As[0][tid >> 5][(tid & 31) * 2]);
+    const unsigned dstB = (unsigned)__cvta_generic_to_shared(&Bs[0][tid / (TW / 2)][(tid % (TW / 2)) * 2]);
+    constexpr unsigned bufA = BULK_KC * BULK_TR * 8, bufB = BULK_KC * TW * 8;   // bytes per stage
+    auto load_chunk = [&](int buf) {   // loads the NEXT chunk (sources advance by 16 rows per call)
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {                       // 16 x 64 doubles
-            const int p = tid + 128 * t;
-            const int kk = p >> 5, part = p & 31;
-            cp_async16(&As[buf][kk][part * 2], a.CpT + (long long)(kk0 + kk) * a.ldc + i0 + part * 2);
-        }
+        for (int t = 0; t < 4; ++t)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dstA + buf * bufA + t * (4 * BULK_TR * 8)),
+                         "l"(srcA + t * stepA));
 #pragma unroll
-        for (int t = 0; t < 2 * CQ; ++t) {                  // 16 x TW doubles
-            const int p = tid + 128 * t;
-            const int kk = p / (TW / 2), part = p % (TW / 2);
-            cp_async16(&Bs[buf][kk][part * 2], a.Rw + (long long)(kk0 + kk) * a.ldw + j0 + part * 2);
-        }
+        for (int t = 0; t < 2 * CQ; ++t)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dstB + buf * bufB + t * ((128 / (TW / 2)) * TW * 8)),
+                         "l"(srcB + t * stepB));
+        srcA += (long long)BULK_KC * a.ldc;
+        srcB += (long long)BULK_KC * a.ldw;
     };
 
-    load_chunk(0, 0);
+    load_chunk(0);
     cp_async_commit();
-    load_chunk(1, 1);
+    load_chunk(1);
     cp_async_commit();
 
     double o[8][NC];
@@ -132,14 +138,15 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
         }
     }
 
-    constexpr int NCH = FW_B / BULK_KC;
+    const int NCH = FW_B / BULK_KC;
+    static_assert(BULK_ST == 3, "buffer rotation below assumes 3 stages");
     int buf = 0;
     for (int ch = 0; ch < NCH; ++ch) {
         // chunk ch has landed once at most one younger group is still in flight
         if (ch + 1 < NCH) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();   // (a) chunk ch visible to all; (b) everyone is done with chunk ch-1's buffer
         if (ch + 2 < NCH) {
-            load_chunk(ch + 2, (buf + 2) % BULK_ST);   // == the buffer chunk ch-1 used
+            load_chunk(buf == 0 ? 2 : buf - 1);        // (buf + 2) % 3 == the buffer chunk ch-1 used
             cp_async_commit();
         }
         // operands of step kk are fetched one step ahead so that their shared-memory latency
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
 #pragma unroll
             for (int c = 0; c < NC; ++c) bv[c] = bvn[c];
         }
-        buf = (buf + 1) % BULK_ST;
+        buf = (buf == BULK_ST - 1) ? 0 : buf + 1;
     }
 
     // ---- epilogue: only entries that were replaced are written back ----
