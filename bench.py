@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=0, help="override the matrix order (debug only)")
+    ap.add_argument("--order", type=int, default=0, help="override the matrix order (debug only)")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--check", action="store_true",
@@ -168,7 +168,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import fw_oracle as O
-    n = workload_n(args.gpus, args.n)
+    n = workload_n(args.gpus, args.order)
     threads = O.max_threads()
     rate, nxt = host_graph(n, SEED)
     ksteps = max(1, int(8 * (32768 / n) ** 2))          # ~8.6e9 relaxations per step
@@ -212,7 +212,7 @@ def run_ours(args):
                                   measured_fp64_peak)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    n = workload_n(1, args.n)
+    n = workload_n(1, args.order)
     peak_tflops, peak_src, peak_raw = measured_fp64_peak()
 
     ctx = _lib.Context(local)

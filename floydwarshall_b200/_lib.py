@@ -27,7 +27,8 @@ SYMBOLS = (
     "fw_ctx_set_stream", "fw_ctx_last_launches", "fw_solve", "fw_solve_device", "fw_solve_batched",
     "fw_solve_batched_device", "fw_ctx_synchronize", "fw_ctx_set_profiling", "fw_ctx_phase_ms",
     "fw_ctx_phase_spans", "fw_shard_validate", "fw_shard_pivot", "fw_shard_update",
-    "fw_paths", "fw_paths_device",
+    "fw_paths", "fw_paths_device", "fw_build_matrix_device", "fw_state_create", "fw_state_destroy",
+    "fw_state_sync", "fw_state_optimum", "fw_state_download",
 )
 
 
@@ -80,6 +81,19 @@ def load():
     L.fw_paths.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i64]
     L.fw_paths_device.restype = ctypes.c_int
     L.fw_paths_device.argtypes = [vp, i32, i64, vp, vp, vp, vp, i32, vp, vp, vp, i64]
+    L.fw_build_matrix_device.restype = ctypes.c_int
+    L.fw_build_matrix_device.argtypes = [vp, i32, i64, vp, i32, vp, vp, vp, vp, vp]
+    L.fw_state_create.restype = ctypes.c_int
+    L.fw_state_create.argtypes = [vp, ctypes.POINTER(vp)]
+    L.fw_state_destroy.restype = None
+    L.fw_state_destroy.argtypes = [vp]
+    L.fw_state_sync.restype = ctypes.c_int
+    L.fw_state_sync.argtypes = [vp, i32, vp, i32, vp, vp, vp]
+    L.fw_state_optimum.restype = ctypes.c_int
+    L.fw_state_optimum.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), vp, i32,
+                                   ctypes.POINTER(i32)]
+    L.fw_state_download.restype = ctypes.c_int
+    L.fw_state_download.argtypes = [vp, vp, vp]
     L.fw_solve.restype = ctypes.c_int
     L.fw_solve.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.fw_solve_device.restype = ctypes.c_int

@@ -92,6 +92,29 @@ __global__ void fw_copy2d_kernel(T *dst, long long dld, const T *src, long long 
     }
 }
 
+// buildMatrix (Algorithms.hs:26-40) on the device, step 1: diagonal and same-currency rule
+__global__ void fw_build_base_kernel(double *rate, int32_t *next, long long ld, int n, const int32_t *ccy) {
+    const long long total = (long long)n * n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / n), j = (int)(e - (long long)i * n);
+        const bool same = (i != j) && (ccy[i] == ccy[j]);          // :33 i == j first, :34 same currency
+        rate[(long long)i * ld + j] = same ? 1.0 : 0.0;
+        next[(long long)i * ld + j] = same ? j : -1;
+    }
+}
+// step 2: the map entries (:35-36) -- never override the diagonal or a same-currency pair
+__global__ void fw_build_edges_kernel(double *rate, int32_t *next, long long ld, int n, const int32_t *ccy,
+                                      int m, const int32_t *src, const int32_t *dst, const double *val, int *flag) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < m; e += gridDim.x * blockDim.x) {
+        const int i = src[e], j = dst[e];
+        if (i < 0 || j < 0 || i >= n || j >= n) { atomicOr(flag, 4); continue; }
+        if (i == j || ccy[i] == ccy[j]) continue;
+        rate[(long long)i * ld + j] = val[e];
+        next[(long long)i * ld + j] = j;
+    }
+}
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
@@ -713,6 +736,155 @@ int fw_paths(fw_ctx *c, int32_t n, const int32_t *init_next, const int32_t *mid,
     rc = fw_paths_device(c, n, n, d[0], d[1], d[2], d[3], nq, queries, offsets, verts, cap);
     for (int j = 0; j < 4; ++j) cudaFree(d[j]);
     return rc;
+}
+
+/* ---- device-side buildMatrix and the resident "InSync" matrix ------------------------------ */
+struct fw_state {
+    fw_ctx *ctx = nullptr;
+    int n = 0;
+    bool synced = false;
+    DevBuf<double> rate;
+    DevBuf<int32_t> next, init_next, mid, csT, rs, ccy, src, dst;
+    DevBuf<double> val;
+};
+
+static int build_matrix_locked(fw_ctx *c, int n, long long ld, const int32_t *d_ccy, int m, const int32_t *d_src,
+                               const int32_t *d_dst, const double *d_val, double *d_rate, int32_t *d_next) {
+    CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+    fw_build_base_kernel<<<grid_for((long long)n * n, c->sm_count), 256, 0, c->stream>>>(d_rate, d_next, ld, n, d_ccy);
+    c->launches++;
+    if (m > 0) {
+        fw_build_edges_kernel<<<grid_for(m, c->sm_count), 256, 0, c->stream>>>(d_rate, d_next, ld, n, d_ccy, m, d_src,
+                                                                                d_dst, d_val, c->d_flag);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    return FW_OK;
+}
+
+int fw_build_matrix_device(fw_ctx *c, int32_t n, int64_t ld, const int32_t *ccy, int32_t m, const int32_t *src,
+                           const int32_t *dst, const double *val, double *d_rate, int32_t *d_next) {
+    if (n < 0 || m < 0) return fail(FW_ERR_INVALID, "fw_build_matrix_device: negative size");
+    if (n == 0) return FW_OK;
+    if (!ccy || !d_rate || !d_next || ld < n || (m > 0 && (!src || !dst || !val)))
+        return fail(FW_ERR_INVALID, "fw_build_matrix_device: bad argument");
+    int rc = get_ctx(c, &c);
+    if (rc != FW_OK) return rc;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->launches = 0;
+    DevBuf<int32_t> dccy, dsrc, ddst; DevBuf<double> dval;
+    auto rel = [&]() { dccy.release(); dsrc.release(); ddst.release(); dval.release(); };
+    if ((rc = dccy.ensure(n)) != FW_OK || (rc = dsrc.ensure(m > 0 ? m : 1)) != FW_OK ||
+        (rc = ddst.ensure(m > 0 ? m : 1)) != FW_OK || (rc = dval.ensure(m > 0 ? m : 1)) != FW_OK) { rel(); return rc; }
+    cudaError_t e = cudaMemcpyAsync(dccy.p, ccy, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && m > 0) e = cudaMemcpyAsync(dsrc.p, src, sizeof(int32_t) * m, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && m > 0) e = cudaMemcpyAsync(ddst.p, dst, sizeof(int32_t) * m, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && m > 0) e = cudaMemcpyAsync(dval.p, val, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream);
+    if (e != cudaSuccess) { rel(); return cuda_fail(e, "fw_build_matrix_device upload"); }
+    rc = build_matrix_locked(c, n, ld, dccy.p, m, dsrc.p, ddst.p, dval.p, d_rate, d_next);
+    if (rc == FW_OK) {
+        e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "fw_build_matrix_device");
+        else if (*c->h_flag & 4) rc = fail(FW_ERR_INVALID, "fw_build_matrix_device: edge endpoint out of range");
+    }
+    rel();
+    return rc;
+}
+
+int fw_state_create(fw_ctx *c, fw_state **out) {
+    if (!out) return fail(FW_ERR_INVALID, "fw_state_create: null output");
+    *out = nullptr;
+    int rc = get_ctx(c, &c);
+    if (rc != FW_OK) return rc;
+    fw_state *s = new (std::nothrow) fw_state();
+    if (!s) return fail(FW_ERR_NOMEM, "out of host memory");
+    s->ctx = c;
+    *out = s;
+    return FW_OK;
+}
+
+void fw_state_destroy(fw_state *s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    s->rate.release(); s->next.release(); s->init_next.release(); s->mid.release(); s->csT.release();
+    s->rs.release(); s->ccy.release(); s->src.release(); s->dst.release(); s->val.release();
+    delete s;
+}
+
+int fw_state_sync(fw_state *s, int32_t n, const int32_t *ccy, int32_t m, const int32_t *src, const int32_t *dst,
+                  const double *val) {
+    if (!s || n < 0 || m < 0) return fail(FW_ERR_INVALID, "fw_state_sync: bad argument");
+    fw_ctx *c = s->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    c->launches = 0;
+    recycle_spans(c);
+    s->synced = false;
+    s->n = n;
+    if (n == 0) { s->synced = true; return FW_OK; }
+    if (!ccy || (m > 0 && (!src || !dst || !val))) return fail(FW_ERR_INVALID, "fw_state_sync: null input");
+    int rc;
+    const size_t tot = (size_t)n * n;
+    if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
+    if ((rc = s->rate.ensure(tot)) != FW_OK || (rc = s->next.ensure(tot)) != FW_OK ||
+        (rc = s->init_next.ensure(tot)) != FW_OK || (rc = s->mid.ensure(tot)) != FW_OK ||
+        (rc = s->csT.ensure(tot)) != FW_OK || (rc = s->rs.ensure(tot)) != FW_OK ||
+        (rc = s->ccy.ensure(n)) != FW_OK || (rc = s->src.ensure(m > 0 ? m : 1)) != FW_OK ||
+        (rc = s->dst.ensure(m > 0 ? m : 1)) != FW_OK || (rc = s->val.ensure(m > 0 ? m : 1)) != FW_OK)
+        return rc;
+    CU(cudaMemcpyAsync(s->ccy.p, ccy, sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+    if (m > 0) {
+        CU(cudaMemcpyAsync(s->src.p, src, sizeof(int32_t) * m, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(s->dst.p, dst, sizeof(int32_t) * m, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(s->val.p, val, sizeof(double) * m, cudaMemcpyHostToDevice, c->stream));
+    }
+    if ((rc = build_matrix_locked(c, n, n, s->ccy.p, m, s->src.p, s->dst.p, s->val.p, s->rate.p, s->next.p)) != FW_OK)
+        return rc;
+    CU(cudaMemcpyAsync(s->init_next.p, s->next.p, tot * 4, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (*c->h_flag & 4) return fail(FW_ERR_INVALID, "fw_state_sync: edge endpoint out of range");
+    if ((rc = solve_device_locked(c, n, n, s->rate.p, s->next.p, s->mid.p, s->csT.p, s->rs.p, true)) != FW_OK)
+        return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    s->synced = true;
+    return FW_OK;
+}
+
+int fw_state_optimum(fw_state *s, int32_t src, int32_t dst, double *rate, int32_t *path, int32_t cap,
+                     int32_t *path_len) {
+    if (!s || !rate || !path_len || cap < 0 || (cap > 0 && !path))
+        return fail(FW_ERR_INVALID, "fw_state_optimum: bad argument");
+    if (!s->synced) return fail(FW_ERR_INVALID, "fw_state_optimum: state is not in sync (call fw_state_sync)");
+    if (src < 0 || dst < 0 || src >= s->n || dst >= s->n) return fail(FW_ERR_INVALID, "fw_state_optimum: vertex index out of range");
+    fw_ctx *c = s->ctx;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        CU(cudaSetDevice(c->device));
+        CU(cudaMemcpyAsync(rate, s->rate.p + (size_t)src * s->n + dst, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    const int32_t q[2] = {src, dst};
+    int64_t off[2] = {0, 0};
+    int rc = fw_paths_device(c, s->n, s->n, s->init_next.p, s->mid.p, s->csT.p, s->rs.p, 1, q, off, path, cap);
+    *path_len = (int32_t)off[1];
+    return rc;
+}
+
+int fw_state_download(fw_state *s, double *rate, int32_t *next) {
+    if (!s || !s->synced) return fail(FW_ERR_INVALID, "fw_state_download: state is not in sync");
+    if (s->n == 0) return FW_OK;
+    fw_ctx *c = s->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CU(cudaSetDevice(c->device));
+    const size_t tot = (size_t)s->n * s->n;
+    if (rate) CU(cudaMemcpyAsync(rate, s->rate.p, tot * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (next) CU(cudaMemcpyAsync(next, s->next.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return FW_OK;
 }
 
 /* ---- row-sharded building blocks (multi-GPU) ------------------------------- */

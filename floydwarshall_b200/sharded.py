@@ -143,7 +143,7 @@ def bench_main(args, METRIC, UNIT, SEED, workload_n, workload_name, ClockSampler
     dev = torch.device("cuda", local)
     if not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
-    n = workload_n(world, args.n)
+    n = workload_n(world, args.order)
     rows = shard_rows(n, world)
     row0 = rank * rows
     peak_tflops, peak_src, peak_raw = measured_fp64_peak() if rank == 0 else (None, None, None)

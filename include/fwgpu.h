@@ -128,6 +128,34 @@ int fw_paths_device(fw_ctx *ctx, int32_t n, int64_t ld, const int32_t *d_init_ne
                     int32_t nq, const int32_t *queries, int64_t *offsets, int32_t *verts,
                     int64_t cap);
 
+/* ---- replaces buildMatrix (Algorithms.hs:26-40) on the device ---------------
+ * The cache in COO form: n vertices in the reference's sorted order
+ * (Algorithms.hs:29), ccy[i] = any integer id of vertex i's currency, m map
+ * entries (src[e], dst[e]) -> val[e] with unique keys (it is a Map).  Rules as in
+ * the reference, in its order: i == j -> (0.0, []); same currency -> (1.0, [j])
+ * BEFORE the map lookup; map hit -> (val, [j]); else (0.0, []).  All inputs are
+ * host arrays; outputs are device matrices with leading dimension ld. */
+int fw_build_matrix_device(fw_ctx *ctx, int32_t n, int64_t ld, const int32_t *ccy, int32_t m,
+                           const int32_t *src, const int32_t *dst, const double *val,
+                           double *d_rate, int32_t *d_next);
+
+/* ---- the InSync state kept on the device (Types.hs:35-37; ProcessRequests.hs:78-85)
+ * fw_state_sync = syncMatrix on an OutSync state: buildMatrix + runAlgo on the
+ * device; the optimised matrix (rate, next and the exact-path tables) STAYS in
+ * HBM.  fw_state_optimum = the read-out of `optimum` (Algorithms.hs:74-75) for
+ * one (src, dst) index pair: *rate = _bestRate, path[0..*path_len) = `_path` as
+ * vertex indices (start excluded); an empty path means "no exchange between".
+ * Only the answer crosses PCIe, never the matrix. */
+typedef struct fw_state fw_state;
+int fw_state_create(fw_ctx *ctx, fw_state **out);
+void fw_state_destroy(fw_state *st);
+int fw_state_sync(fw_state *st, int32_t n, const int32_t *ccy, int32_t m, const int32_t *src,
+                  const int32_t *dst, const double *val);
+int fw_state_optimum(fw_state *st, int32_t src, int32_t dst, double *rate, int32_t *path,
+                     int32_t cap, int32_t *path_len);
+/* Optional full read-back (tests): host rate[n*n] and/or next[n*n]. */
+int fw_state_download(fw_state *st, double *rate, int32_t *next);
+
 /* ---- row-sharded building blocks (one shard per GPU) ----------------------
  * The multi-GPU solve keeps rows [row0, row0+rows) of the n x n
  * matrix on each GPU (n, row0, rows multiples of FW_TILE; ld % 4 == 0).  For

@@ -66,7 +66,7 @@ def test_two_process_nccl_if_two_gpus(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29611",
                           os.path.join(root, "bench.py"), "--gpus", "2", "--steps", "1", "--warmup", "1",
-                          "--n", "2048", "--skip-e2e", "--check"], capture_output=True, text=True, timeout=600)
+                          "--order", "2048", "--skip-e2e", "--check"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
     d = json.loads(line)
