@@ -28,7 +28,7 @@ SYMBOLS = (
     "fw_solve_batched_device", "fw_ctx_synchronize", "fw_ctx_set_profiling", "fw_ctx_phase_ms",
     "fw_ctx_phase_spans", "fw_shard_validate", "fw_shard_pivot", "fw_shard_update",
     "fw_paths", "fw_paths_device", "fw_build_matrix_device", "fw_state_create", "fw_state_destroy",
-    "fw_state_sync", "fw_state_optimum", "fw_state_download",
+    "fw_state_sync", "fw_state_optimum", "fw_state_download", "fw_solve_edges",
 )
 
 
@@ -94,6 +94,8 @@ def load():
                                    ctypes.POINTER(i32)]
     L.fw_state_download.restype = ctypes.c_int
     L.fw_state_download.argtypes = [vp, vp, vp]
+    L.fw_solve_edges.restype = ctypes.c_int
+    L.fw_solve_edges.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.fw_solve.restype = ctypes.c_int
     L.fw_solve.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.fw_solve_device.restype = ctypes.c_int

@@ -64,13 +64,35 @@ def build_matrix(ex_rates: ExRates) -> RateMatrix:
     return RateMatrix(vertices, rate, nxt)
 
 
+def coo(ex_rates: ExRates):
+    """The cache as the C ABI takes it: (vertices, ccy ids i32[n], src i32[m], dst i32[m], val f64[m])."""
+    vertices = sorted_vertices(ex_rates)
+    index = {v: i for i, v in enumerate(vertices)}
+    ccy_ids: Dict[str, int] = {}
+    ccy = np.array([ccy_ids.setdefault(v.ccy, len(ccy_ids)) for v in vertices], dtype=np.int32)
+    m = len(ex_rates)
+    src = np.fromiter((index[s] for (s, _d) in ex_rates), dtype=np.int32, count=m)
+    dst = np.fromiter((index[d] for (_s, d) in ex_rates), dtype=np.int32, count=m)
+    val = np.fromiter(ex_rates.values(), dtype=np.float64, count=m)
+    return vertices, ccy, src, dst, val
+
+
 def floyd_warshall(ex_rates: ExRates, ctx: _lib.Context | None = None) -> RateMatrix:
-    """Algorithms.hs:19-20  floydWarshall = runAlgo 0 . buildMatrix  -- runAlgo on the GPU."""
-    vertices, rate, nxt = pack(ex_rates)
-    if len(vertices) == 0:
-        return RateMatrix(vertices, rate, nxt)              # floydWarshall M.empty == V.empty
-    res = dense.solve(rate, nxt, paths=True, ctx=ctx)       # raises FwError without a GPU: no fallback
-    return RateMatrix(vertices, res.rate, nxt, res.next, res.mid, res.csT, res.rs, ctx=ctx)
+    """Algorithms.hs:19-20  floydWarshall = runAlgo 0 . buildMatrix -- both on the GPU (fw_solve_edges):
+    the map goes up in COO form, the dense matrix and the exact-path tables come back."""
+    import ctypes
+    vertices, ccy, src, dst, val = coo(ex_rates)
+    n = len(vertices)
+    if n == 0:
+        return RateMatrix(vertices, np.zeros((0, 0)), np.zeros((0, 0), dtype=np.int32))   # M.empty -> V.empty
+    rate = np.empty((n, n), dtype=np.float64)
+    out = [np.empty((n, n), dtype=np.int32) for _ in range(5)]      # next, init_next, mid, csT, rs
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+    L = _lib.load()                                                  # raises FwError if not built: no fallback
+    _lib.check(L.fw_solve_edges(ctx.handle if ctx else None, n, vp(ccy), len(src), vp(src), vp(dst), vp(val),
+                                vp(rate), *[vp(a) for a in out]))
+    nxt, init_next, mid, csT, rs = out
+    return RateMatrix(vertices, rate, init_next, nxt, mid, csT, rs, ctx=ctx)
 
 
 def optimum(src: Vertex, dest: Vertex, matrix: Sequence[Sequence[RateEntry]]) -> RateEntry:

@@ -133,8 +133,10 @@ struct DevBuf {
 
 }  // namespace
 
+struct fw_state;
 struct fw_ctx {
     int device = 0;
+    fw_state *edge_state = nullptr;   // cached device state of fw_solve_edges (buffers reused across calls)
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -442,6 +444,7 @@ void fw_ctx_destroy(fw_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->edge_state) { fw_state_destroy(c->edge_state); c->edge_state = nullptr; }
     c->Cp.release(); c->Rw.release(); c->NCp.release();
     c->w_rate.release(); c->w_next.release(); c->w_mid.release(); c->w_csT.release(); c->w_rs.release();
     c->s_rate.release(); c->s_next.release(); c->s_mid.release(); c->s_csT.release(); c->s_rs.release();
@@ -743,6 +746,7 @@ struct fw_state {
     fw_ctx *ctx = nullptr;
     int n = 0;
     bool synced = false;
+    bool want_paths = true;   // keep mid/csT/rs (needed by fw_state_optimum)
     DevBuf<double> rate;
     DevBuf<int32_t> next, init_next, mid, csT, rs, ccy, src, dst;
     DevBuf<double> val;
@@ -829,9 +833,10 @@ int fw_state_sync(fw_state *s, int32_t n, const int32_t *ccy, int32_t m, const i
     int rc;
     const size_t tot = (size_t)n * n;
     if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
+    const bool wp = s->want_paths;
     if ((rc = s->rate.ensure(tot)) != FW_OK || (rc = s->next.ensure(tot)) != FW_OK ||
-        (rc = s->init_next.ensure(tot)) != FW_OK || (rc = s->mid.ensure(tot)) != FW_OK ||
-        (rc = s->csT.ensure(tot)) != FW_OK || (rc = s->rs.ensure(tot)) != FW_OK ||
+        (wp && ((rc = s->init_next.ensure(tot)) != FW_OK || (rc = s->mid.ensure(tot)) != FW_OK ||
+                (rc = s->csT.ensure(tot)) != FW_OK || (rc = s->rs.ensure(tot)) != FW_OK)) ||
         (rc = s->ccy.ensure(n)) != FW_OK || (rc = s->src.ensure(m > 0 ? m : 1)) != FW_OK ||
         (rc = s->dst.ensure(m > 0 ? m : 1)) != FW_OK || (rc = s->val.ensure(m > 0 ? m : 1)) != FW_OK)
         return rc;
@@ -843,11 +848,12 @@ int fw_state_sync(fw_state *s, int32_t n, const int32_t *ccy, int32_t m, const i
     }
     if ((rc = build_matrix_locked(c, n, n, s->ccy.p, m, s->src.p, s->dst.p, s->val.p, s->rate.p, s->next.p)) != FW_OK)
         return rc;
-    CU(cudaMemcpyAsync(s->init_next.p, s->next.p, tot * 4, cudaMemcpyDeviceToDevice, c->stream));
+    if (wp) CU(cudaMemcpyAsync(s->init_next.p, s->next.p, tot * 4, cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (*c->h_flag & 4) return fail(FW_ERR_INVALID, "fw_state_sync: edge endpoint out of range");
-    if ((rc = solve_device_locked(c, n, n, s->rate.p, s->next.p, s->mid.p, s->csT.p, s->rs.p, true)) != FW_OK)
+    if ((rc = solve_device_locked(c, n, n, s->rate.p, s->next.p, wp ? s->mid.p : nullptr, wp ? s->csT.p : nullptr,
+                                  wp ? s->rs.p : nullptr, true)) != FW_OK)
         return rc;
     CU(cudaStreamSynchronize(c->stream));
     s->synced = true;
@@ -859,6 +865,7 @@ int fw_state_optimum(fw_state *s, int32_t src, int32_t dst, double *rate, int32_
     if (!s || !rate || !path_len || cap < 0 || (cap > 0 && !path))
         return fail(FW_ERR_INVALID, "fw_state_optimum: bad argument");
     if (!s->synced) return fail(FW_ERR_INVALID, "fw_state_optimum: state is not in sync (call fw_state_sync)");
+    if (!s->want_paths) return fail(FW_ERR_INVALID, "fw_state_optimum: state was synced without path tables");
     if (src < 0 || dst < 0 || src >= s->n || dst >= s->n) return fail(FW_ERR_INVALID, "fw_state_optimum: vertex index out of range");
     fw_ctx *c = s->ctx;
     {
@@ -885,6 +892,39 @@ int fw_state_download(fw_state *s, double *rate, int32_t *next) {
     if (next) CU(cudaMemcpyAsync(next, s->next.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return FW_OK;
+}
+
+/* floydWarshall :: Map (Vertex, Vertex) Double -> Matrix RateEntry in one call: the cache goes up
+ * as COO (a few MB), buildMatrix + runAlgo run on the device, the dense result comes back. */
+int fw_solve_edges(fw_ctx *c, int32_t n, const int32_t *ccy, int32_t m, const int32_t *src, const int32_t *dst,
+                   const double *val, double *rate, int32_t *next, int32_t *init_next, int32_t *mid, int32_t *csT,
+                   int32_t *rs) {
+    if (n < 0 || m < 0) return fail(FW_ERR_INVALID, "fw_solve_edges: negative size");
+    if (n == 0) return FW_OK;
+    if (!rate || !next) return fail(FW_ERR_INVALID, "fw_solve_edges: null output");
+    if (!paths_args_ok(mid, csT, rs)) return fail(FW_ERR_INVALID, "mid/csT/rs: pass all three or none");
+    int rc = get_ctx(c, &c);
+    if (rc != FW_OK) return rc;
+    if (!c->edge_state && (rc = fw_state_create(c, &c->edge_state)) != FW_OK) return rc;
+    fw_state *st = c->edge_state;
+    st->want_paths = (mid != nullptr) || (init_next != nullptr);
+    rc = fw_state_sync(st, n, ccy, m, src, dst, val);
+    if (rc == FW_OK) {
+        fw_ctx *cc = st->ctx;
+        std::lock_guard<std::mutex> lk(cc->mu);
+        const size_t tot = (size_t)n * n;
+        cudaError_t e = cudaMemcpyAsync(rate, st->rate.p, tot * 8, cudaMemcpyDeviceToHost, cc->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(next, st->next.p, tot * 4, cudaMemcpyDeviceToHost, cc->stream);
+        if (e == cudaSuccess && init_next) e = cudaMemcpyAsync(init_next, st->init_next.p, tot * 4, cudaMemcpyDeviceToHost, cc->stream);
+        if (e == cudaSuccess && mid) {
+            e = cudaMemcpyAsync(mid, st->mid.p, tot * 4, cudaMemcpyDeviceToHost, cc->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(csT, st->csT.p, tot * 4, cudaMemcpyDeviceToHost, cc->stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(rs, st->rs.p, tot * 4, cudaMemcpyDeviceToHost, cc->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cc->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "fw_solve_edges download");
+    }
+    return rc;
 }
 
 /* ---- row-sharded building blocks (multi-GPU) ------------------------------- */

@@ -53,15 +53,9 @@ class ResidentMatrix:
 
     def __init__(self, ex_rates: Dict[Tuple[Vertex, Vertex], float], ctx: Optional[_lib.Context] = None):
         L = _lib.load()
-        self.vertices = algorithms.sorted_vertices(ex_rates)
+        self.vertices, ccy, src, dst, val = algorithms.coo(ex_rates)
         self.index = {v: i for i, v in enumerate(self.vertices)}
-        n = len(self.vertices)
-        ccy_ids: Dict[str, int] = {}
-        ccy = np.array([ccy_ids.setdefault(v.ccy, len(ccy_ids)) for v in self.vertices], dtype=np.int32)
-        m = len(ex_rates)
-        src = np.fromiter((self.index[s] for (s, _d) in ex_rates), dtype=np.int32, count=m)
-        dst = np.fromiter((self.index[d] for (_s, d) in ex_rates), dtype=np.int32, count=m)
-        val = np.fromiter(ex_rates.values(), dtype=np.float64, count=m)
+        n, m = len(self.vertices), len(src)
         h = ctypes.c_void_p()
         _lib.check(L.fw_state_create(ctx.handle if ctx else None, ctypes.byref(h)))
         self._h, self.n = h, n

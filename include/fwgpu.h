@@ -139,6 +139,15 @@ int fw_build_matrix_device(fw_ctx *ctx, int32_t n, int64_t ld, const int32_t *cc
                            const int32_t *src, const int32_t *dst, const double *val,
                            double *d_rate, int32_t *d_next);
 
+/* floydWarshall (Algorithms.hs:19-20) in ONE call, map in / dense matrix out: the
+ * cache goes up in COO form (as fw_build_matrix_device), buildMatrix + runAlgo
+ * run on the device, the dense result lands in the HOST outputs rate[n*n],
+ * next[n*n] and, if non-NULL, init_next (the buildMatrix next-hops) and the
+ * exact-path tables mid/csT/rs (all three or none). */
+int fw_solve_edges(fw_ctx *ctx, int32_t n, const int32_t *ccy, int32_t m, const int32_t *src,
+                   const int32_t *dst, const double *val, double *rate, int32_t *next,
+                   int32_t *init_next, int32_t *mid, int32_t *csT, int32_t *rs);
+
 /* ---- the InSync state kept on the device (Types.hs:35-37; ProcessRequests.hs:78-85)
  * fw_state_sync = syncMatrix on an OutSync state: buildMatrix + runAlgo on the
  * device; the optimised matrix (rate, next and the exact-path tables) STAYS in
