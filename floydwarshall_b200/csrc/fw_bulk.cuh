@@ -34,16 +34,22 @@ struct BulkArgs {
     int32_t *next;
     int32_t *mid;          // nullable
     long long ld;
-    int npad;              // number of columns
-    int b0;                // first pivot of the k-block (global)
-    int rows;              // rows held by this shard
-    int row0;              // global index of local row 0
-    int blk_r0;            // LOCAL row of pivot b0, INT_MAX if the shard does not hold it
-    const double *CpT;     // B x rows  column snapshots, transposed: CpT[kk*ldc + i]
-    long long ldc;
-    const int32_t *NCp;    // rows x B  next-hop snapshots: NCp[i*B + kk]
-    const double *Rw;      // B x N     row snapshots: Rw[kk*ldw + j]
-    long long ldw;
+    int b0;                // first pivot of the (first) k-block (global)
+    int row0;              // global index of local row 0 (row shards; 0 otherwise)
+    // One launch applies nb (1 or 2) CONSECUTIVE k-blocks [b0, b0 + nb*128) to every selected tile,
+    // from per-block snapshot panels:
+    int nb;
+    const double *CpT[2];  // B x rows  column snapshots, transposed: CpT[kk*ldc + i]
+    const int32_t *NCp[2]; // rows x B  next-hop snapshots: NCp[i*B + kk]
+    const double *Rw[2];   // B x N     row snapshots: Rw[kk*ldw + j]
+    long long ldc, ldw;
+    // Tile selection, in tile units (64 local rows / TW columns): grid (x, y) -> tile
+    //   tj = col_lo + x, += cskipn if tj >= cskip0;   ti = row_lo + y, += rskipn if ti >= rskip0
+    int row_lo, rskip0, rskipn;
+    int col_lo, cskip0, cskipn;   // in units of 64 columns (scaled by 64/TW inside the kernel)
+    // nb == 2: tiles in the strips of the FIRST block (tile rows [half_r0, half_r0+2) or tile columns
+    // of the first block) already took its 128 steps in phase 2 and only run the second block's.
+    int half_r0, half_c0;         // tile row / 64-column unit of the first block; huge if none
 };
 
 constexpr int BULK_TR = 64;   // tile rows
@@ -78,39 +84,44 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
 
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
-    const int tbc = a.b0 / TW;              // first tile column covered by the k-block
-    const int tbr = a.blk_r0 / BULK_TR;     // first LOCAL tile row covered (huge if none)
-    int ti = blockIdx.y, tj = blockIdx.x;
-    ti = ti < tbr ? ti : ti + FW_B / BULK_TR;
-    tj = tj < tbc ? tj : tj + FW_B / TW;
+    constexpr int CU = TW / 64;             // 64-column units per tile column
+    int ti = a.row_lo + (int)blockIdx.y, tj = a.col_lo / CU + (int)blockIdx.x;
+    if (ti >= a.rskip0) ti += a.rskipn;
+    if (tj >= a.cskip0 / CU) tj += a.cskipn / CU;
     const int i0 = ti * BULK_TR, j0 = tj * TW;
+    int kstart = 0;
+    if (a.nb == 2 && ((ti >= a.half_r0 && ti < a.half_r0 + FW_B / BULK_TR) ||
+                      (tj >= a.half_c0 / CU && tj < a.half_c0 / CU + FW_B / TW)))
+        kstart = FW_B;
     const long long ld = a.ld;
 
     // cp.async sources/destinations of this thread, computed once: piece p = tid + 128*t covers
     // A: row kk = (tid>>5) + 4t, 16 bytes at column (tid&31)*2;  B: likewise with TW/2 pieces per row.
-    const double *srcA = a.CpT + (long long)(tid >> 5) * a.ldc + i0 + (tid & 31) * 2;
-    const double *srcB = a.Rw + (long long)(tid / (TW / 2)) * a.ldw + j0 + (tid % (TW / 2)) * 2;
-    const long long stepA = 4 * a.ldc;                      // +4 rows per t
-    const long long stepB = (long long)(128 / (TW / 2)) * a.ldw;
+    // 32-bit element offsets of this thread's first piece inside a panel (panels are < 2^31 elements)
+    const int offA = (tid >> 5) * (int)a.ldc + i0 + (tid & 31) * 2;
+    const int offB = (tid / (TW / 2)) * (int)a.ldw + j0 + (tid % (TW / 2)) * 2;
     const unsigned dstA = (unsigned)__cvta_generic_to_shared(&As[0][tid >> 5][(tid & 31) * 2]);
     const unsigned dstB = (unsigned)__cvta_generic_to_shared(&Bs[0][tid / (TW / 2)][(tid % (TW / 2)) * 2]);
     constexpr unsigned bufA = BULK_KC * BULK_TR * 8, bufB = BULK_KC * TW * 8;   // bytes per stage
-    auto load_chunk = [&](int buf) {   // loads the NEXT chunk (sources advance by 16 rows per call)
+    // chunk c (0 .. nb*8-1) = steps [16c, 16c+16) relative to b0; chunks 8.. come from the second block's panels
+    auto load_chunk = [&](int c, int buf) {
+        const int set = c >> 3, kk0 = (c & 7) * BULK_KC;
+        const double *pa = a.CpT[set] + ((long long)kk0 * a.ldc + offA);
+        const double *pb = a.Rw[set] + ((long long)kk0 * a.ldw + offB);
 #pragma unroll
         for (int t = 0; t < 4; ++t)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dstA + buf * bufA + t * (4 * BULK_TR * 8)),
-                         "l"(srcA + t * stepA));
+                         "l"(pa + (long long)t * 4 * a.ldc));
 #pragma unroll
         for (int t = 0; t < 2 * CQ; ++t)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dstB + buf * bufB + t * ((128 / (TW / 2)) * TW * 8)),
-                         "l"(srcB + t * stepB));
-        srcA += (long long)BULK_KC * a.ldc;
-        srcB += (long long)BULK_KC * a.ldw;
+                         "l"(pb + (long long)t * (128 / (TW / 2)) * a.ldw));
     };
 
-    load_chunk(0);
+    const int ch0 = kstart / BULK_KC, ch1 = a.nb * (FW_B / BULK_KC);
+    load_chunk(ch0, 0);
     cp_async_commit();
-    load_chunk(1);
+    load_chunk(ch0 + 1, 1);
     cp_async_commit();
 
     double o[8][NC];
@@ -120,9 +131,6 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
         const long long ro = (long long)(i0 + ty * 8 + r) * ld + j0 + tx * 2;
 #pragma unroll
         for (int cq = 0; cq < CQ; ++cq) {
-            // two 8-byte loads, not one 16-byte load: a vector load would pin o[r][2cq], o[r][2cq+1] to
-            // the same register-bank pairs as the LDS.128-loaded b operands they meet in the DFMAs
-            // (2-way operand bank conflict on every DFMA, measured: 55 % of the DFMA rate)
             o[r][cq * 2] = __ldg(a.rate + ro + cq * 32);
             o[r][cq * 2 + 1] = __ldg(a.rate + ro + cq * 32 + 1);
         }
@@ -138,15 +146,14 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
         }
     }
 
-    const int NCH = FW_B / BULK_KC;
     static_assert(BULK_ST == 3, "buffer rotation below assumes 3 stages");
     int buf = 0;
-    for (int ch = 0; ch < NCH; ++ch) {
+    for (int ch = ch0; ch < ch1; ++ch) {
         // chunk ch has landed once at most one younger group is still in flight
-        if (ch + 1 < NCH) cp_async_wait<1>(); else cp_async_wait<0>();
+        if (ch + 1 < ch1) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();   // (a) chunk ch visible to all; (b) everyone is done with chunk ch-1's buffer
-        if (ch + 2 < NCH) {
-            load_chunk(buf == 0 ? 2 : buf - 1);        // (buf + 2) % 3 == the buffer chunk ch-1 used
+        if (ch + 2 < ch1) {
+            load_chunk(ch + 2, buf == 0 ? 2 : buf - 1);   // (buf + 2) % 3 == the buffer chunk ch-1 used
             cp_async_commit();
         }
         // operands of step kk are fetched one step ahead so that their shared-memory latency
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
             for (int r = 0; r < 8; ++r) accr[r] = and_tree<NC>(hi[r]);
             const int acc = and_tree<8>(accr);
             if (__builtin_expect(__any_sync(0xffffffffu, acc >= 0), 0)) {
-                const int kloc = ch * BULK_KC + kk;
+                const int kloc = ch * BULK_KC + kk;   // step index relative to b0 (0..255)
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     if (__any_sync(0xffffffffu, accr[r] >= 0)) {
@@ -226,12 +233,12 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
                 }
                 if (cb & 1u) {
                     const int m0 = Ms[r * NC + cq * 2][tid];
-                    a.next[eo] = a.NCp[(long long)row * FW_B + m0];
+                    a.next[eo] = a.NCp[m0 >> 7][(long long)row * FW_B + (m0 & (FW_B - 1))];
                     if (a.mid) a.mid[eo] = a.b0 + m0;
                 }
                 if (cb & 2u) {
                     const int m1 = Ms[r * NC + cq * 2 + 1][tid];
-                    a.next[eo + 1] = a.NCp[(long long)row * FW_B + m1];
+                    a.next[eo + 1] = a.NCp[m1 >> 7][(long long)row * FW_B + (m1 & (FW_B - 1))];
                     if (a.mid) a.mid[eo + 1] = a.b0 + m1;
                 }
             }

@@ -143,8 +143,9 @@ struct fw_ctx {
     std::mutex mu;
     int64_t launches = 0;
     // snapshot panels
-    DevBuf<double> Cp, Rw;
-    DevBuf<int32_t> NCp;
+    DevBuf<double> Cp[2], Rw[2];   // two panel sets: k-blocks are processed in pairs
+    DevBuf<int32_t> NCp[2];
+    bool fuse_pairs = true;        // knob FW_FUSE_PAIRS=0 turns pairing off
     // padded working copy (n not a multiple of FW_B) and host-API staging
     DevBuf<double> w_rate;
     DevBuf<int32_t> w_next, w_mid, w_csT, w_rs;
@@ -185,6 +186,7 @@ int set_kernel_attrs(fw_ctx *c) {
                             (int)fw::bulk_smem_bytes<4>()));
     CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     if (const char *e = getenv("FW_BULK_CQ")) c->bulk_cq = atoi(e) == 4 ? 4 : 2;
+    if (const char *e = getenv("FW_FUSE_PAIRS")) c->fuse_pairs = atoi(e) != 0;
     c->attrs_set = true;
     return FW_OK;
 }
@@ -218,16 +220,21 @@ int grid_for(long long total, int sm_count) {
     return (int)g;
 }
 
-void launch_bulk(fw_ctx *c, const fw::BulkArgs &g, int ncols, int rows_out) {
+// Tile ranges are given in 64-row / 64-column units (see fw::BulkArgs); ncu = units of columns, nru = of rows.
+void launch_bulk(fw_ctx *c, const fw::BulkArgs &g, int ncu, int nru) {
+    if (ncu <= 0 || nru <= 0) return;
     PhaseTimer pt(c, 3);
     if (c->bulk_cq == 4) {
-        const dim3 grid(ncols / 128 - 1, rows_out / fw::BULK_TR);
+        const dim3 grid(ncu / 2, nru);
         fw::fw_bulk_kernel<4><<<grid, 128, fw::bulk_smem_bytes<4>(), c->stream>>>(g);
     } else {
-        const dim3 grid(ncols / 64 - 2, rows_out / fw::BULK_TR);
+        const dim3 grid(ncu, nru);
         fw::fw_bulk_kernel<2><<<grid, 128, fw::bulk_smem_bytes<2>(), c->stream>>>(g);
     }
+    c->launches++;
 }
+
+constexpr int NOSKIP = 0x3fffffff;
 
 // Domain check (synchronises the stream once).
 int validate_device(fw_ctx *c, const double *rate, const int32_t *next, long long ld, long long stride,
@@ -246,53 +253,94 @@ int validate_device(fw_ctx *c, const double *rate, const int32_t *next, long lon
     return FW_OK;
 }
 
+// Phase 1 + 2 of k-block b0 into panel set `set`: diagonal tile, column panel, row panel.
+int launch_pivot_phases(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next, int32_t *mid, int32_t *csT,
+                        int32_t *rs, int b0, int set, bool panels) {
+    const bool paths = (mid != nullptr);
+    fw::TileArgs t;
+    t.rate = rate; t.next = next; t.mid = mid; t.csT = csT; t.rs = rs;
+    t.ld = ld; t.batch_stride = 0; t.b0 = b0; t.r0 = b0; t.nv = FW_B;
+    t.Cp = c->Cp[set].p; t.ldc = npad; t.NCp = c->NCp[set].p; t.Rw = c->Rw[set].p; t.ldw = npad;
+    {
+        PhaseTimer pt(c, 0);
+        if (paths)
+            fw::fw_tile_kernel<true><<<1, 512, fw::tile_smem_bytes(true), c->stream>>>(t);
+        else
+            fw::fw_tile_kernel<false><<<1, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
+    }
+    c->launches++;
+    if (panels) {
+        const int njobs32 = (npad - FW_B) / 32;
+        const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
+        fw::PanelArgs p;
+        p.rate = rate; p.next = next; p.mid = mid; p.csT = csT; p.rs = rs;
+        p.ld = ld; p.npad = npad; p.b0 = b0; p.rows = npad; p.blk_r0 = b0;
+        p.Cp = c->Cp[set].p; p.ldc = npad; p.NCp = c->NCp[set].p; p.Rw = c->Rw[set].p; p.ldw = npad;
+        {
+            PhaseTimer pt(c, 1);
+            if (paths) fw::fw_colpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+            else fw::fw_colpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+        }
+        {
+            PhaseTimer pt(c, 2);
+            if (paths) fw::fw_rowpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+            else fw::fw_rowpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+        }
+        c->launches += 2;
+    }
+    CU(cudaGetLastError());
+    return FW_OK;
+}
+
 // Blocked solve on a padded (npad % FW_B == 0, pads = NaN) device matrix.
+//
+// k-blocks are taken in PAIRS (b, b+1) so that the bulk kernel loads every tile once per 256 steps:
+//   phases 1+2 of b  ->  bulk(b) on the strips of b+1 only (they are b+1's pivot rows/columns and
+//   must be current)  ->  phases 1+2 of b+1  ->  one fused bulk launch: 256 steps for tiles outside
+//   both strips, the second 128 for tiles in b's strips (phase 2 of b already gave them the first).
+// The order of relaxations seen by every entry is unchanged (ascending k), so results are identical.
 int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next, int32_t *mid,
                   int32_t *csT, int32_t *rs) {
-    const bool paths = (mid != nullptr);
     int rc;
-    if ((rc = c->Cp.ensure((size_t)npad * FW_B)) != FW_OK) return rc;
-    if ((rc = c->NCp.ensure((size_t)npad * FW_B)) != FW_OK) return rc;
-    if ((rc = c->Rw.ensure((size_t)npad * FW_B)) != FW_OK) return rc;
+    for (int set = 0; set < 2; ++set) {
+        if ((rc = c->Cp[set].ensure((size_t)npad * FW_B)) != FW_OK) return rc;
+        if ((rc = c->NCp[set].ensure((size_t)npad * FW_B)) != FW_OK) return rc;
+        if ((rc = c->Rw[set].ensure((size_t)npad * FW_B)) != FW_OK) return rc;
+    }
     const int nblk = npad / FW_B;
-    const int njobs32 = (npad - FW_B) / 32;
-    const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
-    for (int b = 0; b < nblk; ++b) {
-        const int b0 = b * FW_B;
-        fw::TileArgs t;
-        t.rate = rate; t.next = next; t.mid = mid; t.csT = csT; t.rs = rs;
-        t.ld = ld; t.batch_stride = 0; t.b0 = b0; t.r0 = b0; t.nv = FW_B;
-        t.Cp = c->Cp.p; t.ldc = npad; t.NCp = c->NCp.p; t.Rw = c->Rw.p; t.ldw = npad;
-        {
-            PhaseTimer pt(c, 0);
-            if (paths)
-                fw::fw_tile_kernel<true><<<1, 512, fw::tile_smem_bytes(true), c->stream>>>(t);
-            else
-                fw::fw_tile_kernel<false><<<1, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
-        }
-        c->launches++;
-        if (nblk > 1) {
-            fw::PanelArgs p;
-            p.rate = rate; p.next = next; p.mid = mid; p.csT = csT; p.rs = rs;
-            p.ld = ld; p.npad = npad; p.b0 = b0; p.rows = npad; p.blk_r0 = b0;
-            p.Cp = c->Cp.p; p.ldc = npad; p.NCp = c->NCp.p; p.Rw = c->Rw.p; p.ldw = npad;
-            {
-                PhaseTimer pt(c, 1);
-                if (paths) fw::fw_colpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
-                else fw::fw_colpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
-            }
-            {
-                PhaseTimer pt(c, 2);
-                if (paths) fw::fw_rowpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
-                else fw::fw_rowpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
-            }
-            c->launches += 2;
-            fw::BulkArgs g;
-            g.rate = rate; g.next = next; g.mid = mid; g.ld = ld; g.npad = npad; g.b0 = b0;
-            g.rows = npad; g.row0 = 0; g.blk_r0 = b0;
-            g.CpT = c->Cp.p; g.ldc = npad; g.NCp = c->NCp.p; g.Rw = c->Rw.p; g.ldw = npad;
-            launch_bulk(c, g, npad, npad - FW_B);
-            c->launches++;
+    const int nu = npad / 64;                 // 64-row / 64-column units
+    fw::BulkArgs g;
+    g.rate = rate; g.next = next; g.mid = mid; g.ld = ld; g.row0 = 0; g.ldc = npad; g.ldw = npad;
+    for (int set = 0; set < 2; ++set) { g.CpT[set] = c->Cp[set].p; g.NCp[set] = c->NCp[set].p; g.Rw[set] = c->Rw[set].p; }
+    int b = 0;
+    while (b < nblk) {
+        const int b0 = b * FW_B, u0 = b0 / 64;
+        if ((rc = launch_pivot_phases(c, npad, ld, rate, next, mid, csT, rs, b0, 0, nblk > 1)) != FW_OK) return rc;
+        if (nblk == 1) break;
+        const bool pair = c->fuse_pairs && (b + 1 < nblk);
+        g.b0 = b0;
+        if (!pair) {
+            g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
+            g.row_lo = 0; g.rskip0 = u0; g.rskipn = 2;
+            g.col_lo = 0; g.cskip0 = u0; g.cskipn = 2;
+            launch_bulk(c, g, nu - 2, nu - 2);
+            b += 1;
+        } else {
+            // bulk(b) on the strips of block b+1
+            g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
+            g.row_lo = u0 + 2; g.rskip0 = NOSKIP; g.rskipn = 0;          // the 2 tile rows of b+1 ...
+            g.col_lo = 0; g.cskip0 = u0; g.cskipn = 2;                   // ... x all columns outside b
+            launch_bulk(c, g, nu - 2, 2);
+            g.row_lo = 0; g.rskip0 = u0; g.rskipn = 4;                   // all rows outside b and b+1 ...
+            g.col_lo = u0 + 2; g.cskip0 = NOSKIP; g.cskipn = 0;          // ... x the 2 tile columns of b+1
+            launch_bulk(c, g, 2, nu - 4);
+            if ((rc = launch_pivot_phases(c, npad, ld, rate, next, mid, csT, rs, b0 + FW_B, 1, true)) != FW_OK) return rc;
+            // fused: everything outside the strips of b+1
+            g.nb = 2; g.half_r0 = u0; g.half_c0 = u0;
+            g.row_lo = 0; g.rskip0 = u0 + 2; g.rskipn = 2;
+            g.col_lo = 0; g.cskip0 = u0 + 2; g.cskipn = 2;
+            launch_bulk(c, g, nu - 2, nu - 2);
+            b += 2;
         }
         CU(cudaGetLastError());
     }
@@ -445,7 +493,7 @@ void fw_ctx_destroy(fw_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->edge_state) { fw_state_destroy(c->edge_state); c->edge_state = nullptr; }
-    c->Cp.release(); c->Rw.release(); c->NCp.release();
+    for (int i = 0; i < 2; ++i) { c->Cp[i].release(); c->Rw[i].release(); c->NCp[i].release(); }
     c->w_rate.release(); c->w_next.release(); c->w_mid.release(); c->w_csT.release(); c->w_rs.release();
     c->s_rate.release(); c->s_next.release(); c->s_mid.release(); c->s_csT.release(); c->s_rs.release();
     if (c->d_flag) cudaFree(c->d_flag);
@@ -955,15 +1003,15 @@ int fw_shard_pivot(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld,
     CU(cudaSetDevice(c->device));
     int rc;
     if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
-    if ((rc = c->Cp.ensure((size_t)rows * FW_B)) != FW_OK) return rc;
-    if ((rc = c->NCp.ensure((size_t)rows * FW_B)) != FW_OK) return rc;
+    if ((rc = c->Cp[0].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
+    if ((rc = c->NCp[0].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
     c->launches = 0;
     recycle_spans(c);
     const int blk_r0 = b0 - row0;
     fw::TileArgs t;
     t.rate = d_rate; t.next = d_next; t.mid = nullptr; t.csT = nullptr; t.rs = nullptr;
     t.ld = ld; t.batch_stride = 0; t.b0 = b0; t.r0 = blk_r0; t.nv = FW_B;
-    t.Cp = c->Cp.p; t.ldc = rows; t.NCp = c->NCp.p; t.Rw = d_Rw; t.ldw = n;
+    t.Cp = c->Cp[0].p; t.ldc = rows; t.NCp = c->NCp[0].p; t.Rw = d_Rw; t.ldw = n;
     {
         PhaseTimer pt(c, 0);
         fw::fw_tile_kernel<false><<<1, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
@@ -973,7 +1021,7 @@ int fw_shard_pivot(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld,
         fw::PanelArgs p;
         p.rate = d_rate; p.next = d_next; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
         p.ld = ld; p.npad = n; p.b0 = b0; p.rows = rows; p.blk_r0 = blk_r0;
-        p.Cp = c->Cp.p; p.ldc = rows; p.NCp = c->NCp.p; p.Rw = d_Rw; p.ldw = n;
+        p.Cp = c->Cp[0].p; p.ldc = rows; p.NCp = c->NCp[0].p; p.Rw = d_Rw; p.ldw = n;
         const int njobs32 = (n - FW_B) / 32;
         const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
         PhaseTimer pt(c, 2);
@@ -992,8 +1040,8 @@ int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld
     CU(cudaSetDevice(c->device));
     int rc;
     if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
-    if ((rc = c->Cp.ensure((size_t)rows * FW_B)) != FW_OK) return rc;
-    if ((rc = c->NCp.ensure((size_t)rows * FW_B)) != FW_OK) return rc;
+    if ((rc = c->Cp[0].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
+    if ((rc = c->NCp[0].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
     const bool owner = (b0 >= row0 && b0 < row0 + rows);
     if (!owner) { c->launches = 0; recycle_spans(c); }   // the owner keeps counting after fw_shard_pivot
     const int blk_r0 = owner ? b0 - row0 : 0x7fffffff;
@@ -1002,7 +1050,7 @@ int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld
         fw::PanelArgs p;
         p.rate = d_rate; p.next = d_next; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
         p.ld = ld; p.npad = n; p.b0 = b0; p.rows = rows; p.blk_r0 = blk_r0;
-        p.Cp = c->Cp.p; p.ldc = rows; p.NCp = c->NCp.p; p.Rw = const_cast<double *>(d_Rw); p.ldw = n;
+        p.Cp = c->Cp[0].p; p.ldc = rows; p.NCp = c->NCp[0].p; p.Rw = const_cast<double *>(d_Rw); p.ldw = n;
         const int njobs32 = rows_out / 32;
         const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
         {
@@ -1011,11 +1059,14 @@ int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld
         }
         c->launches++;
         fw::BulkArgs g;
-        g.rate = d_rate; g.next = d_next; g.mid = nullptr; g.ld = ld; g.npad = n; g.b0 = b0;
-        g.rows = rows; g.row0 = row0; g.blk_r0 = blk_r0;
-        g.CpT = c->Cp.p; g.ldc = rows; g.NCp = c->NCp.p; g.Rw = d_Rw; g.ldw = n;
-        launch_bulk(c, g, n, rows_out);
-        c->launches++;
+        g.rate = d_rate; g.next = d_next; g.mid = nullptr; g.ld = ld; g.b0 = b0; g.row0 = row0;
+        g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
+        g.CpT[0] = c->Cp[0].p; g.NCp[0] = c->NCp[0].p; g.Rw[0] = d_Rw;
+        g.CpT[1] = nullptr; g.NCp[1] = nullptr; g.Rw[1] = nullptr;
+        g.ldc = rows; g.ldw = n;
+        g.row_lo = 0; g.rskip0 = owner ? blk_r0 / 64 : NOSKIP; g.rskipn = owner ? 2 : 0;
+        g.col_lo = 0; g.cskip0 = b0 / 64; g.cskipn = 2;
+        launch_bulk(c, g, n / 64 - 2, rows_out / 64);
     }
     CU(cudaGetLastError());
     return FW_OK;
