@@ -31,7 +31,9 @@ struct PanelArgs {
     int npad;       // padded matrix order = number of columns (multiple of FW_B)
     int b0;         // first pivot of the k-block (global index)
     int rows;       // rows held by this shard (== npad when unsharded)
-    int blk_r0;     // LOCAL row of pivot b0 if this shard holds the k-block rows, else INT_MAX
+    int blk_r0;     // LOCAL row of pivot b0 if this shard holds the k-block rows (row panel), else INT_MAX
+    int skip_r0;    // column panel: local rows [skip_r0, skip_r0 + skipn) are left out (INT_MAX: none)
+    int skipn;
     double *Cp;     // B x rows column snapshots, TRANSPOSED: Cp[kk*ldc + i]
     long long ldc;
     int32_t *NCp;
@@ -56,10 +58,10 @@ __global__ void __launch_bounds__(512, 1) fw_colpanel_kernel(PanelArgs a) {
     __syncthreads();
 
     const int job = tid >> 4, l = tid & 15;
-    const int nrows = a.rows - (a.blk_r0 < a.rows ? FW_B : 0);
+    const int nrows = a.rows - (a.skip_r0 < a.rows ? a.skipn : 0);
     for (int g = blockIdx.x; g * 32 < nrows; g += gridDim.x) {
         const int rp = g * 32 + job;
-        const int i = rp < a.blk_r0 ? rp : rp + FW_B;   // local row, skipping the k-block rows
+        const int i = rp < a.skip_r0 ? rp : rp + a.skipn;   // local row, skipping the k-block rows
         const long long off = (long long)i * a.ld + b0 + l * 8;
         double y[8], cs[8];
         int nx[8], ncs[8], md[8], mcs[8];

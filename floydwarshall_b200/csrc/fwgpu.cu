@@ -274,7 +274,7 @@ int launch_pivot_phases(fw_ctx *c, int npad, long long ld, double *rate, int32_t
         const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
         fw::PanelArgs p;
         p.rate = rate; p.next = next; p.mid = mid; p.csT = csT; p.rs = rs;
-        p.ld = ld; p.npad = npad; p.b0 = b0; p.rows = npad; p.blk_r0 = b0;
+        p.ld = ld; p.npad = npad; p.b0 = b0; p.rows = npad; p.blk_r0 = b0; p.skip_r0 = b0; p.skipn = FW_B;
         p.Cp = c->Cp[set].p; p.ldc = npad; p.NCp = c->NCp[set].p; p.Rw = c->Rw[set].p; p.ldw = npad;
         {
             PhaseTimer pt(c, 1);
@@ -1020,7 +1020,7 @@ int fw_shard_pivot(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld,
     if (n > FW_B) {
         fw::PanelArgs p;
         p.rate = d_rate; p.next = d_next; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
-        p.ld = ld; p.npad = n; p.b0 = b0; p.rows = rows; p.blk_r0 = blk_r0;
+        p.ld = ld; p.npad = n; p.b0 = b0; p.rows = rows; p.blk_r0 = blk_r0; p.skip_r0 = blk_r0; p.skipn = FW_B;
         p.Cp = c->Cp[0].p; p.ldc = rows; p.NCp = c->NCp[0].p; p.Rw = d_Rw; p.ldw = n;
         const int njobs32 = (n - FW_B) / 32;
         const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
@@ -1032,10 +1032,14 @@ int fw_shard_pivot(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld,
     return FW_OK;
 }
 
-int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
-                    int32_t *d_next, int32_t b0, const double *d_Rw) {
+/* mode 0: every local row outside the k-block; mode 1: ONLY the 128 local rows starting at lr0;
+ * mode 2: every local row outside the k-block and outside the 128 rows starting at lr0. */
+int fw_shard_update_ex(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
+                       int32_t *d_next, int32_t b0, const double *d_Rw, int32_t mode, int32_t lr0) {
     if (!c || !shard_args_ok(n, row0, rows, ld, d_rate, d_next, b0, d_Rw))
         return fail(FW_ERR_INVALID, "fw_shard_update: bad argument (sizes must be multiples of 128, 16-byte aligned)");
+    if (mode < 0 || mode > 2 || (mode != 0 && (lr0 < 0 || lr0 % FW_B || lr0 + FW_B > rows)))
+        return fail(FW_ERR_INVALID, "fw_shard_update_ex: bad mode / row range");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     int rc;
@@ -1043,33 +1047,58 @@ int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld
     if ((rc = c->Cp[0].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
     if ((rc = c->NCp[0].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
     const bool owner = (b0 >= row0 && b0 < row0 + rows);
-    if (!owner) { c->launches = 0; recycle_spans(c); }   // the owner keeps counting after fw_shard_pivot
-    const int blk_r0 = owner ? b0 - row0 : 0x7fffffff;
-    const int rows_out = rows - (owner ? FW_B : 0);
-    if (rows_out > 0 && n > FW_B) {
-        fw::PanelArgs p;
-        p.rate = d_rate; p.next = d_next; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
-        p.ld = ld; p.npad = n; p.b0 = b0; p.rows = rows; p.blk_r0 = blk_r0;
-        p.Cp = c->Cp[0].p; p.ldc = rows; p.NCp = c->NCp[0].p; p.Rw = const_cast<double *>(d_Rw); p.ldw = n;
-        const int njobs32 = rows_out / 32;
-        const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
-        {
-            PhaseTimer pt(c, 1);
-            fw::fw_colpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+    const int blk_r0 = owner ? b0 - row0 : -1;
+    if (mode != 0 && owner && lr0 == blk_r0) return fail(FW_ERR_INVALID, "fw_shard_update_ex: lr0 is the k-block itself");
+    c->launches = 0;
+    recycle_spans(c);
+    // The rows to process form the sub-shard [v0, v0 + vrows) minus one skip range [s0, s0 + sn)  (local rows)
+    int v0 = 0, vrows = rows, s0 = NOSKIP, sn = 0;
+    if (mode == 1) {
+        v0 = lr0; vrows = FW_B;
+    } else {
+        if (owner) { s0 = blk_r0; sn = FW_B; }
+        if (mode == 2) {
+            if (!owner) { s0 = lr0; sn = FW_B; }
+            else if (lr0 == blk_r0 + FW_B) { sn = 2 * FW_B; }
+            else if (lr0 + FW_B == blk_r0) { s0 = lr0; sn = 2 * FW_B; }
+            else return fail(FW_ERR_INVALID, "fw_shard_update_ex: mode 2 needs lr0 adjacent to the k-block rows");
         }
-        c->launches++;
-        fw::BulkArgs g;
-        g.rate = d_rate; g.next = d_next; g.mid = nullptr; g.ld = ld; g.b0 = b0; g.row0 = row0;
-        g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
-        g.CpT[0] = c->Cp[0].p; g.NCp[0] = c->NCp[0].p; g.Rw[0] = d_Rw;
-        g.CpT[1] = nullptr; g.NCp[1] = nullptr; g.Rw[1] = nullptr;
-        g.ldc = rows; g.ldw = n;
-        g.row_lo = 0; g.rskip0 = owner ? blk_r0 / 64 : NOSKIP; g.rskipn = owner ? 2 : 0;
-        g.col_lo = 0; g.cskip0 = b0 / 64; g.cskipn = 2;
-        launch_bulk(c, g, n / 64 - 2, rows_out / 64);
     }
+    const int rows_out = vrows - sn;
+    if (rows_out <= 0 || n <= FW_B) return FW_OK;
+    // kernels see the sub-shard as a shard of its own: pointers and row origin shifted by v0
+    double *rate_v = d_rate + (long long)v0 * ld;
+    int32_t *next_v = d_next + (long long)v0 * ld;
+    double *cp_v = c->Cp[0].p + v0;                       // CpT[kk*ldc + i]
+    int32_t *ncp_v = c->NCp[0].p + (long long)v0 * FW_B;  // NCp[i*B + kk]
+    const int s0v = (s0 == NOSKIP) ? NOSKIP : s0 - v0;
+    fw::PanelArgs p;
+    p.rate = rate_v; p.next = next_v; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
+    p.ld = ld; p.npad = n; p.b0 = b0; p.rows = vrows; p.blk_r0 = NOSKIP; p.skip_r0 = s0v; p.skipn = sn;
+    p.Cp = cp_v; p.ldc = rows; p.NCp = ncp_v; p.Rw = const_cast<double *>(d_Rw); p.ldw = n;
+    const int njobs32 = rows_out / 32;
+    const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
+    {
+        PhaseTimer pt(c, 1);
+        fw::fw_colpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+    }
+    c->launches++;
+    fw::BulkArgs g;
+    g.rate = rate_v; g.next = next_v; g.mid = nullptr; g.ld = ld; g.b0 = b0; g.row0 = row0 + v0;
+    g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
+    g.CpT[0] = cp_v; g.NCp[0] = ncp_v; g.Rw[0] = d_Rw;
+    g.CpT[1] = nullptr; g.NCp[1] = nullptr; g.Rw[1] = nullptr;
+    g.ldc = rows; g.ldw = n;
+    g.row_lo = 0; g.rskip0 = (s0v == NOSKIP) ? NOSKIP : s0v / 64; g.rskipn = sn / 64;
+    g.col_lo = 0; g.cskip0 = b0 / 64; g.cskipn = 2;
+    launch_bulk(c, g, n / 64 - 2, rows_out / 64);
     CU(cudaGetLastError());
     return FW_OK;
+}
+
+int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
+                    int32_t *d_next, int32_t b0, const double *d_Rw) {
+    return fw_shard_update_ex(c, n, row0, rows, ld, d_rate, d_next, b0, d_Rw, 0, 0);
 }
 
 }  // extern "C"

@@ -25,6 +25,7 @@ import numpy as np
 from . import _lib
 
 B = _lib.FW_TILE
+LOOKAHEAD = os.environ.get("FW_LOOKAHEAD", "1") != "0"   # pivot-panel look-ahead on a second stream
 
 
 def shard_rows(n: int, world: int) -> int:
@@ -46,6 +47,126 @@ def run_schedule(backend, n: int, rank: int, world: int, bcast: Callable[[int], 
         backend.update(b0)
 
 
+def run_schedule_lookahead(backend, n: int, rank: int, world: int, rt) -> None:
+    """Same result as run_schedule, but the owner of k-block b+1 brings that block's 128 pivot rows
+    up to date FIRST (on the look-ahead lane), factors them and starts their broadcast while every
+    rank is still busy with the bulk of k-block b.  `rt` provides the two lanes:
+
+        rt.lane_b()            context manager: work issued inside goes to the look-ahead lane
+        rt.a_done() / rt.wait_a_done()   main lane finished update(b)  /  look-ahead lane waits for it
+        rt.b_done() / rt.wait_b_done()   Rw(b+1) has arrived           /  main lane waits for it
+        rt.bcast(buf, owner)   broadcast backend.Rw[buf] from `owner` (collective, look-ahead lane)
+
+    Program order is a valid serial order, so a synchronous runtime (tests) gives the same answer.
+    """
+    rows = shard_rows(n, world)
+    nblk = n // B
+    if rank == 0:
+        with rt.lane_b():
+            backend.pivot(0, 0)
+    if world > 1:
+        with rt.lane_b():
+            rt.bcast(0, 0)
+    rt.b_done()
+    for b in range(nblk):
+        b0, buf = b * B, b & 1
+        nxt = b + 1 < nblk
+        own_next = nxt and ((b0 + B) // rows == rank)
+        lr_next = (b0 + B) - rank * rows
+        rt.wait_b_done()                      # Rw(b) is here (and the early rows are current)
+        if nxt:
+            with rt.lane_b():
+                rt.wait_a_done()              # update(b-1) finished: rows of b+1 and buffer buf^1 are free
+                if own_next:
+                    backend.update(b0, buf, 1, lr_next)       # only the next pivot rows
+                    backend.pivot(b0 + B, buf ^ 1)
+                if world > 1:
+                    rt.bcast(buf ^ 1, (b0 + B) // rows)
+                rt.b_done()
+        backend.update(b0, buf, 2 if own_next else 0, lr_next if own_next else 0)
+        rt.a_done()
+
+
+class SerialRuntime:
+    """Both lanes are the caller's thread (CPU tests): events are no-ops."""
+
+    def __init__(self, bcast):
+        self._bcast = bcast
+
+    class _Null:
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+    def lane_b(self):
+        return self._Null()
+
+    def a_done(self): pass
+    def wait_a_done(self): pass
+    def b_done(self): pass
+    def wait_b_done(self): pass
+
+    def bcast(self, buf, owner):
+        self._bcast(buf, owner)
+
+
+class TorchRuntime:
+    """Main lane = the current stream, look-ahead lane = a second CUDA stream; NCCL broadcast."""
+
+    def __init__(self, backend, world):
+        import torch
+        self.torch = torch
+        self.be = backend
+        self.world = world
+        self.sa = torch.cuda.current_stream()
+        self.sb = torch.cuda.Stream()
+        self.sb.wait_stream(self.sa)
+        self.ev_a = None
+        self.ev_b = None
+
+    def lane_b(self):
+        rt = self
+
+        class _Lane:
+            def __enter__(self_inner):
+                rt.be.ctx.set_stream(rt.sb.cuda_stream)
+                self_inner.cm = rt.torch.cuda.stream(rt.sb)
+                self_inner.cm.__enter__()
+
+            def __exit__(self_inner, *a):
+                self_inner.cm.__exit__(*a)
+                rt.be.ctx.set_stream(rt.sa.cuda_stream)
+                return False
+
+        return _Lane()
+
+    def a_done(self):
+        self.ev_a = self.torch.cuda.Event()
+        self.ev_a.record(self.sa)
+
+    def wait_a_done(self):
+        if self.ev_a is not None:
+            self.sb.wait_event(self.ev_a)
+
+    def b_done(self):
+        self.ev_b = self.torch.cuda.Event()
+        self.ev_b.record(self.sb)
+
+    def wait_b_done(self):
+        if self.ev_b is not None:
+            self.sa.wait_event(self.ev_b)
+
+    def bcast(self, buf, owner):
+        import torch.distributed as dist
+        dist.broadcast(self.be.Rw2[buf], src=owner)
+
+    def finish(self):
+        self.sa.wait_stream(self.sb)
+        self.be.ctx.set_stream(self.sa.cuda_stream)
+
+
 class GpuShardBackend:
     """Local rows of the matrix as torch CUDA tensors + the fw_shard_* entry points."""
 
@@ -55,7 +176,8 @@ class GpuShardBackend:
         assert rate_t.shape[1] == n and rate_t.dtype == torch.float64 and next_t.dtype == torch.int32
         self.ctx, self.n, self.row0, self.rows = ctx, n, row0, rate_t.shape[0]
         self.rate, self.next = rate_t, next_t
-        self.Rw = torch.empty((B, n), dtype=torch.float64, device=rate_t.device)
+        self.Rw2 = [torch.empty((B, n), dtype=torch.float64, device=rate_t.device) for _ in range(2)]
+        self.Rw = self.Rw2[0]
         self.L = _lib.load()
         self.launches = 0
 
@@ -66,14 +188,27 @@ class GpuShardBackend:
         _lib.check(self.L.fw_shard_validate(self.ctx.handle, self.n, self.row0, self.rows, self.n,
                                             self._p(self.rate), self._p(self.next)))
 
-    def pivot(self, b0: int):
+    def pivot(self, b0: int, buf: int = 0):
         _lib.check(self.L.fw_shard_pivot(self.ctx.handle, self.n, self.row0, self.rows, self.n,
-                                         self._p(self.rate), self._p(self.next), b0, self._p(self.Rw)))
-
-    def update(self, b0: int):
-        _lib.check(self.L.fw_shard_update(self.ctx.handle, self.n, self.row0, self.rows, self.n,
-                                          self._p(self.rate), self._p(self.next), b0, self._p(self.Rw)))
+                                         self._p(self.rate), self._p(self.next), b0, self._p(self.Rw2[buf])))
         self.launches += self.ctx.last_launches
+
+    def update(self, b0: int, buf: int = 0, mode: int = 0, lr0: int = 0):
+        _lib.check(self.L.fw_shard_update_ex(self.ctx.handle, self.n, self.row0, self.rows, self.n,
+                                             self._p(self.rate), self._p(self.next), b0, self._p(self.Rw2[buf]),
+                                             mode, lr0))
+        self.launches += self.ctx.last_launches
+
+
+def solve_shard(backend, n: int, rank: int, world: int, lookahead: bool = True):
+    """Run the k-block schedule on a GpuShardBackend (collective: call on every rank)."""
+    import torch.distributed as dist
+    if lookahead:
+        rt = TorchRuntime(backend, world)
+        run_schedule_lookahead(backend, n, rank, world, rt)
+        rt.finish()
+    else:
+        run_schedule(backend, n, rank, world, lambda owner: dist.broadcast(backend.Rw, src=owner))
 
 
 def solve_sharded_device(ctx: _lib.Context, n: int, rate_t, next_t, validate: bool = True):
@@ -86,7 +221,7 @@ def solve_sharded_device(ctx: _lib.Context, n: int, rate_t, next_t, validate: bo
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     if validate:
         be.validate()
-    run_schedule(be, n, rank, world, lambda owner: dist.broadcast(be.Rw, src=owner))
+    solve_shard(be, n, rank, world, lookahead=LOOKAHEAD)
     return be
 
 
@@ -159,7 +294,7 @@ def bench_main(args, METRIC, UNIT, SEED, workload_n, workload_name, ClockSampler
         r.copy_(r0)
         x.copy_(x0)
         be.validate()
-        run_schedule(be, n, rank, world, lambda owner: dist.broadcast(be.Rw, src=owner))
+        solve_shard(be, n, rank, world, lookahead=LOOKAHEAD)
 
     for _ in range(args.warmup):
         step()
@@ -256,6 +391,7 @@ def bench_main(args, METRIC, UNIT, SEED, workload_n, workload_name, ClockSampler
             "config": {"workload": workload_name(n), "n": n, "seed": SEED + 1, "k_block": B,
                        "sharding": f"row blocks of {rows} rows per rank; per-k-block NCCL broadcast of the "
                                    f"128 x {n} fp64 pivot-row snapshot panel ({B * n * 8 / 2**20:.0f} MiB)",
+                       "lookahead": LOOKAHEAD,
                        "l2": "per-rank inputs are far larger than the 126 MB L2; no flush needed",
                        "check": check},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()),

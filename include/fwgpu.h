@@ -181,6 +181,13 @@ int fw_shard_pivot(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t l
                    double *d_rate, int32_t *d_next, int32_t b0, double *d_Rw);
 int fw_shard_update(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
                     double *d_rate, int32_t *d_next, int32_t b0, const double *d_Rw);
+/* Look-ahead variant: mode 0 = fw_shard_update; mode 1 = ONLY the 128 local rows starting at
+ * lr0 (the next k-block's pivot rows, so its owner can factor them early on a second stream);
+ * mode 2 = everything mode 0 does EXCEPT those 128 rows (lr0 must be adjacent to the k-block
+ * rows when the shard owns them). */
+int fw_shard_update_ex(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
+                       double *d_rate, int32_t *d_next, int32_t b0, const double *d_Rw,
+                       int32_t mode, int32_t lr0);
 
 /* Block until everything queued on the context's stream has finished and
  * report any asynchronous failure (incl. FW_ERR_DOMAIN of *_device calls). */

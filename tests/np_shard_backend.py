@@ -10,7 +10,8 @@ class NumpyShardBackend:
     def __init__(self, n, row0, rate, nxt, block=B):
         self.n, self.row0, self.rows, self.B = n, row0, rate.shape[0], block
         self.rate, self.next = rate, nxt
-        self.Rw = np.zeros((block, n))
+        self.Rw2 = [np.zeros((block, n)), np.zeros((block, n))]
+        self.Rw = self.Rw2[0]
         self.Cp = np.zeros((self.rows, block))
         self.NCp = np.zeros((self.rows, block), dtype=np.int32)
         # the diagonal is held as NaN while solving (see csrc/fw_common.cuh) and restored by finish()
@@ -29,8 +30,9 @@ class NumpyShardBackend:
         R[upd] = nv[upd]
         X[upd] = np.broadcast_to(an[:, None], R.shape)[upd]
 
-    def pivot(self, b0):
+    def pivot(self, b0, buf=0):
         B_ = self.B
+        Rw = self.Rw2[buf]
         lr = b0 - self.row0
         ks = slice(b0, b0 + B_)
         D = self.rate[lr:lr + B_, ks]
@@ -38,7 +40,7 @@ class NumpyShardBackend:
         for kk in range(B_):
             self.Cp[lr:lr + B_, kk] = D[:, kk]
             self.NCp[lr:lr + B_, kk] = DX[:, kk]
-            self.Rw[kk, ks] = D[kk, :]
+            Rw[kk, ks] = D[kk, :]
             self._relax(D, DX, D[:, kk].copy(), DX[:, kk].copy(), D[kk, :].copy())
         out = np.ones(self.n, bool)
         out[ks] = False
@@ -52,19 +54,27 @@ class NumpyShardBackend:
             self._relax(Xr, XX, Cd[:, kk], NCd[:, kk], Xr[kk].copy())
         self.rate[lr:lr + B_, out] = Xr
         self.next[lr:lr + B_, out] = XX
-        self.Rw[:, out] = Rwo
+        Rw[:, out] = Rwo
 
-    def update(self, b0):
+    def update(self, b0, buf=0, mode=0, lr0=0):
+        """mode 0: all rows outside the k-block; 1: only rows [lr0, lr0+B); 2: mode 0 minus those rows."""
         B_ = self.B
+        Rw = self.Rw2[buf]
         ks = slice(b0, b0 + B_)
         rout = np.ones(self.rows, bool)
         if self.row0 <= b0 < self.row0 + self.rows:
             rout[b0 - self.row0:b0 - self.row0 + B_] = False
+        if mode == 1:
+            only = np.zeros(self.rows, bool)
+            only[lr0:lr0 + B_] = True
+            rout &= only
+        elif mode == 2:
+            rout[lr0:lr0 + B_] = False
         if not rout.any():
             return
         Y = self.rate[rout][:, ks]
         YX = self.next[rout][:, ks]
-        Rd = self.Rw[:, ks]
+        Rd = Rw[:, ks]
         Cc = np.empty((Y.shape[0], B_))
         NCc = np.empty((Y.shape[0], B_), dtype=np.int32)
         for kk in range(B_):
@@ -82,6 +92,6 @@ class NumpyShardBackend:
         Rb = self.rate[np.ix_(ridx, cidx)]
         Xb = self.next[np.ix_(ridx, cidx)]
         for kk in range(B_):
-            self._relax(Rb, Xb, self.Cp[ridx, kk], self.NCp[ridx, kk], self.Rw[kk, cidx])
+            self._relax(Rb, Xb, self.Cp[ridx, kk], self.NCp[ridx, kk], Rw[kk, cidx])
         self.rate[np.ix_(ridx, cidx)] = Rb
         self.next[np.ix_(ridx, cidx)] = Xb

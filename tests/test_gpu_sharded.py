@@ -11,9 +11,10 @@ from oracle import fw_oracle as O
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("lookahead", [False, True])
 @pytest.mark.parametrize("world,E,C,mode", [(1, 24, 16, "consistent"), (2, 32, 16, "consistent"),
                                             (4, 32, 16, "arbitrage"), (2, 16, 16, "pow2")])
-def test_virtual_ranks_on_one_gpu(world, E, C, mode):
+def test_virtual_ranks_on_one_gpu(world, E, C, mode, lookahead):
     import torch
     n = E * C
     rate, nxt = graphs.exchange_graph(E, C, seed=31, density=0.7, mode=mode)
@@ -29,14 +30,37 @@ def test_virtual_ranks_on_one_gpu(world, E, C, mode):
         be = sharded.GpuShardBackend(ctxs[r], n, r * rows, rt, xt)
         be.validate()
         bes.append(be)
-    for b0 in range(0, n, sharded.B):
-        owner = b0 // rows
-        bes[owner].pivot(b0)
-        for r in range(world):
-            if r != owner:
-                bes[r].Rw.copy_(bes[owner].Rw)      # stands in for dist.broadcast(Rw, src=owner)
-        for r in range(world):
-            bes[r].update(b0)
+    if not lookahead:
+        for b0 in range(0, n, sharded.B):
+            owner = b0 // rows
+            bes[owner].pivot(b0)
+            for r in range(world):
+                if r != owner:
+                    bes[r].Rw.copy_(bes[owner].Rw)      # stands in for dist.broadcast(Rw, src=owner)
+            for r in range(world):
+                bes[r].update(b0)
+    else:
+        # the look-ahead call sequence (fw_shard_update_ex modes 1/2), serialised on one stream
+        nblk = n // sharded.B
+        bes[0].pivot(0, 0)
+        for r in range(1, world):
+            bes[r].Rw2[0].copy_(bes[0].Rw2[0])
+        for b in range(nblk):
+            b0, buf = b * sharded.B, b & 1
+            nxt = b + 1 < nblk
+            on = (b0 + sharded.B) // rows if nxt else -1
+            if nxt:
+                lr = (b0 + sharded.B) - on * rows
+                bes[on].update(b0, buf, 1, lr)
+                bes[on].pivot(b0 + sharded.B, buf ^ 1)
+                for r in range(world):
+                    if r != on:
+                        bes[r].Rw2[buf ^ 1].copy_(bes[on].Rw2[buf ^ 1])
+            for r in range(world):
+                if r == on:
+                    bes[r].update(b0, buf, 2, (b0 + sharded.B) - r * rows)
+                else:
+                    bes[r].update(b0, buf, 0, 0)
     torch.cuda.synchronize()
     got_r = np.concatenate([be.rate.cpu().numpy() for be in bes])
     got_x = np.concatenate([be.next.cpu().numpy() for be in bes])

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, n, block, mode, out_dir):
+def _worker(rank, world, port, n, block, mode, out_dir, lookahead=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch
@@ -31,9 +31,16 @@ def _worker(rank, world, port, n, block, mode, out_dir):
         t = torch.from_numpy(be.Rw)
         dist.broadcast(t, src=owner)
 
+    def bcast2(buf, owner):
+        t = torch.from_numpy(be.Rw2[buf])
+        dist.broadcast(t, src=owner)
+
     sharded.B = block      # the schedule is block-size agnostic; shrink it so the test is fast
     try:
-        sharded.run_schedule(be, n, rank, world, bcast)
+        if lookahead:
+            sharded.run_schedule_lookahead(be, n, rank, world, sharded.SerialRuntime(bcast2))
+        else:
+            sharded.run_schedule(be, n, rank, world, bcast)
     finally:
         sharded.B = 128
     be.finish()
@@ -43,13 +50,14 @@ def _worker(rank, world, port, n, block, mode, out_dir):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("lookahead", [False, True])
 @pytest.mark.parametrize("mode", ["consistent", "arbitrage"])
-def test_two_rank_schedule_matches_oracle(tmp_path, mode):
+def test_two_rank_schedule_matches_oracle(tmp_path, mode, lookahead):
     from floydwarshall_b200 import graphs
     from oracle import fw_oracle as O
     n, block, world = 64, 8, 2
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, n, block, mode, str(tmp_path)), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 2000) + (7 if lookahead else 0)
+    mp.spawn(_worker, args=(world, port, n, block, mode, str(tmp_path), lookahead), nprocs=world, join=True)
     rate, nxt = graphs.exchange_graph(n // 8, 8, seed=21, density=0.8, mode=mode)
     ref = O.solve_dense(rate, nxt)
     got_r = np.concatenate([np.load(tmp_path / f"rate{r}.npy") for r in range(world)])
