@@ -121,7 +121,7 @@ class TorchRuntime:
         self.be = backend
         self.world = world
         self.sa = torch.cuda.current_stream()
-        self.sb = torch.cuda.Stream()
+        self.sb = torch.cuda.Stream(priority=-1)   # high priority: its CTAs cut in front of the bulk kernel
         self.sb.wait_stream(self.sa)
         self.ev_a = None
         self.ev_b = None
