@@ -139,12 +139,16 @@ struct fw_ctx {
     fw_state *edge_state = nullptr;   // cached device state of fw_solve_edges (buffers reused across calls)
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // high priority: pivot phases of the NEXT k-blocks overlap the bulk kernel
+    cudaStream_t cur = nullptr;           // stream the launch helpers use right now (stream or side_stream)
+    cudaEvent_t ev_main = nullptr, ev_side = nullptr;
+    bool overlap = true;                  // knob FW_OVERLAP=0: everything on one stream
     cudaStream_t stream = nullptr;
     std::mutex mu;
     int64_t launches = 0;
     // snapshot panels
-    DevBuf<double> Cp[2], Rw[2];   // two panel sets: k-blocks are processed in pairs
-    DevBuf<int32_t> NCp[2];
+    DevBuf<double> Cp[4], Rw[4];   // panel sets: k-blocks go in pairs, and the next pair is factored ahead
+    DevBuf<int32_t> NCp[4];
     bool fuse_pairs = true;        // knob FW_FUSE_PAIRS=0 turns pairing off
     // padded working copy (n not a multiple of FW_B) and host-API staging
     DevBuf<double> w_rate;
@@ -199,11 +203,11 @@ struct PhaseTimer {
         if (!c->pool.empty()) { s = c->pool.back(); c->pool.pop_back(); }
         else { cudaEventCreate(&s.a); cudaEventCreate(&s.b); }
         s.phase = phase;
-        cudaEventRecord(s.a, c->stream);
+        cudaEventRecord(s.a, c->cur ? c->cur : c->stream);
     }
     ~PhaseTimer() {
         if (!on) return;
-        cudaEventRecord(s.b, c->stream);
+        cudaEventRecord(s.b, c->cur ? c->cur : c->stream);
         c->spans.push_back(s);
     }
 };
@@ -226,10 +230,10 @@ void launch_bulk(fw_ctx *c, const fw::BulkArgs &g, int ncu, int nru) {
     PhaseTimer pt(c, 3);
     if (c->bulk_cq == 4) {
         const dim3 grid(ncu / 2, nru);
-        fw::fw_bulk_kernel<4><<<grid, 128, fw::bulk_smem_bytes<4>(), c->stream>>>(g);
+        fw::fw_bulk_kernel<4><<<grid, 128, fw::bulk_smem_bytes<4>(), (c->cur ? c->cur : c->stream)>>>(g);
     } else {
         const dim3 grid(ncu, nru);
-        fw::fw_bulk_kernel<2><<<grid, 128, fw::bulk_smem_bytes<2>(), c->stream>>>(g);
+        fw::fw_bulk_kernel<2><<<grid, 128, fw::bulk_smem_bytes<2>(), (c->cur ? c->cur : c->stream)>>>(g);
     }
     c->launches++;
 }
@@ -242,7 +246,7 @@ int validate_device(fw_ctx *c, const double *rate, const int32_t *next, long lon
     if (rows < 0) rows = n;
     CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
     const long long total = (long long)batch * rows * n;
-    fw_validate_kernel<<<grid_for(total, c->sm_count), 256, 0, c->stream>>>(rate, next, ld, stride, rows, n, row0,
+    fw_validate_kernel<<<grid_for(total, c->sm_count), 256, 0, (c->cur ? c->cur : c->stream)>>>(rate, next, ld, stride, rows, n, row0,
                                                                              total, c->d_flag);
     c->launches++;
     CU(cudaGetLastError());
@@ -264,9 +268,9 @@ int launch_pivot_phases(fw_ctx *c, int npad, long long ld, double *rate, int32_t
     {
         PhaseTimer pt(c, 0);
         if (paths)
-            fw::fw_tile_kernel<true><<<1, 512, fw::tile_smem_bytes(true), c->stream>>>(t);
+            fw::fw_tile_kernel<true><<<1, 512, fw::tile_smem_bytes(true), (c->cur ? c->cur : c->stream)>>>(t);
         else
-            fw::fw_tile_kernel<false><<<1, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
+            fw::fw_tile_kernel<false><<<1, 512, fw::tile_smem_bytes(false), (c->cur ? c->cur : c->stream)>>>(t);
     }
     c->launches++;
     if (panels) {
@@ -278,13 +282,13 @@ int launch_pivot_phases(fw_ctx *c, int npad, long long ld, double *rate, int32_t
         p.Cp = c->Cp[set].p; p.ldc = npad; p.NCp = c->NCp[set].p; p.Rw = c->Rw[set].p; p.ldw = npad;
         {
             PhaseTimer pt(c, 1);
-            if (paths) fw::fw_colpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
-            else fw::fw_colpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+            if (paths) fw::fw_colpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), (c->cur ? c->cur : c->stream)>>>(p);
+            else fw::fw_colpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), (c->cur ? c->cur : c->stream)>>>(p);
         }
         {
             PhaseTimer pt(c, 2);
-            if (paths) fw::fw_rowpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
-            else fw::fw_rowpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+            if (paths) fw::fw_rowpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), (c->cur ? c->cur : c->stream)>>>(p);
+            else fw::fw_rowpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), (c->cur ? c->cur : c->stream)>>>(p);
         }
         c->launches += 2;
     }
@@ -294,56 +298,99 @@ int launch_pivot_phases(fw_ctx *c, int npad, long long ld, double *rate, int32_t
 
 // Blocked solve on a padded (npad % FW_B == 0, pads = NaN) device matrix.
 //
-// k-blocks are taken in PAIRS (b, b+1) so that the bulk kernel loads every tile once per 256 steps:
-//   phases 1+2 of b  ->  bulk(b) on the strips of b+1 only (they are b+1's pivot rows/columns and
-//   must be current)  ->  phases 1+2 of b+1  ->  one fused bulk launch: 256 steps for tiles outside
-//   both strips, the second 128 for tiles in b's strips (phase 2 of b already gave them the first).
-// The order of relaxations seen by every entry is unchanged (ascending k), so results are identical.
+// k-blocks are taken in GROUPS of two (b, b+1) so that the bulk kernel loads every tile once per
+// 256 steps, and the pivot phases of the NEXT group run on a high-priority side stream while the
+// bulk of the current group is still busy:
+//
+//   main stream : bulk(G) on the strips of G'  | record E1 |  bulk(G) on everything else
+//   side stream :                    wait E1 -> phases 1+2 of b', bulk(b') on the strips of b'+1,
+//                                               phases 1+2 of b'+1 | record E2          (G' = {b', b'+1})
+//   next group  : main waits E2
+//
+// bulk(G) gives tiles outside both strips of G 256 steps and tiles in the first block's strips the
+// second 128 (phase 2 of the first block already gave them the first).  The order of relaxations
+// seen by every entry is unchanged (ascending k), so results are identical to the plain loop.
 int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next, int32_t *mid,
                   int32_t *csT, int32_t *rs) {
     int rc;
-    for (int set = 0; set < 2; ++set) {
+    for (int set = 0; set < 4; ++set) {
         if ((rc = c->Cp[set].ensure((size_t)npad * FW_B)) != FW_OK) return rc;
         if ((rc = c->NCp[set].ensure((size_t)npad * FW_B)) != FW_OK) return rc;
         if ((rc = c->Rw[set].ensure((size_t)npad * FW_B)) != FW_OK) return rc;
     }
     const int nblk = npad / FW_B;
     const int nu = npad / 64;                 // 64-row / 64-column units
+    const int gsz = c->fuse_pairs ? 2 : 1;
+    cudaStream_t S = c->stream;
+    cudaStream_t T = (c->overlap && c->side_stream) ? c->side_stream : c->stream;
+    const bool two = (T != S);
     fw::BulkArgs g;
     g.rate = rate; g.next = next; g.mid = mid; g.ld = ld; g.row0 = 0; g.ldc = npad; g.ldw = npad;
-    for (int set = 0; set < 2; ++set) { g.CpT[set] = c->Cp[set].p; g.NCp[set] = c->NCp[set].p; g.Rw[set] = c->Rw[set].p; }
-    int b = 0;
-    while (b < nblk) {
+    auto use_sets = [&](int s0) {
+        for (int i = 0; i < 2; ++i) {
+            g.CpT[i] = c->Cp[s0 + i].p; g.NCp[i] = c->NCp[s0 + i].p; g.Rw[i] = c->Rw[s0 + i].p;
+        }
+    };
+    // phases 1+2 of the group starting at block b (gn blocks) into panel sets s0, s0+1 -- on c->cur
+    auto pivot_group = [&](int b, int gn, int s0) -> int {
         const int b0 = b * FW_B, u0 = b0 / 64;
-        if ((rc = launch_pivot_phases(c, npad, ld, rate, next, mid, csT, rs, b0, 0, nblk > 1)) != FW_OK) return rc;
-        if (nblk == 1) break;
-        const bool pair = c->fuse_pairs && (b + 1 < nblk);
-        g.b0 = b0;
-        if (!pair) {
-            g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
-            g.row_lo = 0; g.rskip0 = u0; g.rskipn = 2;
-            g.col_lo = 0; g.cskip0 = u0; g.cskipn = 2;
-            launch_bulk(c, g, nu - 2, nu - 2);
-            b += 1;
+        int r = launch_pivot_phases(c, npad, ld, rate, next, mid, csT, rs, b0, s0, nblk > 1);
+        if (r != FW_OK || gn == 1) return r;
+        use_sets(s0);
+        g.b0 = b0; g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
+        g.row_lo = u0 + 2; g.rskip0 = NOSKIP; g.rskipn = 0;          // the 2 tile rows of b+1 ...
+        g.col_lo = 0; g.cskip0 = u0; g.cskipn = 2;                   // ... x all columns outside b
+        launch_bulk(c, g, nu - 2, 2);
+        g.row_lo = 0; g.rskip0 = u0; g.rskipn = 4;                   // all rows outside b and b+1 ...
+        g.col_lo = u0 + 2; g.cskip0 = NOSKIP; g.cskipn = 0;          // ... x the 2 tile columns of b+1
+        launch_bulk(c, g, 2, nu - 4);
+        return launch_pivot_phases(c, npad, ld, rate, next, mid, csT, rs, b0 + FW_B, s0 + 1, true);
+    };
+
+    if (two) { CU(cudaEventRecord(c->ev_main, S)); CU(cudaStreamWaitEvent(T, c->ev_main, 0)); }
+    int b = 0, sbase = 0;
+    int gn = (nblk - b < gsz) ? nblk - b : gsz;
+    c->cur = T;
+    if ((rc = pivot_group(b, gn, sbase)) != FW_OK) { c->cur = nullptr; return rc; }
+    if (two) CU(cudaEventRecord(c->ev_side, T));
+    while (b < nblk && nblk > 1) {
+        const int b0 = b * FW_B, u0 = b0 / 64;
+        const int bn = b + gn;                                          // first block of the next group
+        const int gnn = (nblk - bn < gsz) ? nblk - bn : gsz;            // its size (0: none)
+        const int uL = u0 + 2 * (gn - 1);                               // units of the LAST block of this group
+        c->cur = S;
+        if (two) CU(cudaStreamWaitEvent(S, c->ev_side, 0));             // panels of this group are ready
+        use_sets(sbase);
+        g.b0 = b0; g.nb = gn;
+        g.half_r0 = (gn == 2) ? u0 : NOSKIP; g.half_c0 = (gn == 2) ? u0 : NOSKIP;
+        if (gnn > 0) {
+            const int uN = uL + 2;                                      // units of the next group: [uN, uN + 2*gnn)
+            // (1) the next group's pivot rows / columns first
+            g.row_lo = uN; g.rskip0 = NOSKIP; g.rskipn = 0;
+            g.col_lo = 0; g.cskip0 = uL; g.cskipn = 2;
+            launch_bulk(c, g, nu - 2, 2 * gnn);
+            g.row_lo = 0; g.rskip0 = uL; g.rskipn = 2 + 2 * gnn;
+            g.col_lo = uN; g.cskip0 = NOSKIP; g.cskipn = 0;
+            launch_bulk(c, g, 2 * gnn, nu - 2 - 2 * gnn);
+            if (two) { CU(cudaEventRecord(c->ev_main, S)); CU(cudaStreamWaitEvent(T, c->ev_main, 0)); }
+            // (2) everything else of this group's bulk ...
+            g.row_lo = 0; g.rskip0 = uL; g.rskipn = 2 + 2 * gnn;
+            g.col_lo = 0; g.cskip0 = uL; g.cskipn = 2 + 2 * gnn;
+            launch_bulk(c, g, nu - 2 - 2 * gnn, nu - 2 - 2 * gnn);
+            // ... while the side stream factors the next group
+            c->cur = T;
+            if ((rc = pivot_group(bn, gnn, sbase ^ 2)) != FW_OK) { c->cur = nullptr; return rc; }
+            if (two) CU(cudaEventRecord(c->ev_side, T));
         } else {
-            // bulk(b) on the strips of block b+1
-            g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
-            g.row_lo = u0 + 2; g.rskip0 = NOSKIP; g.rskipn = 0;          // the 2 tile rows of b+1 ...
-            g.col_lo = 0; g.cskip0 = u0; g.cskipn = 2;                   // ... x all columns outside b
-            launch_bulk(c, g, nu - 2, 2);
-            g.row_lo = 0; g.rskip0 = u0; g.rskipn = 4;                   // all rows outside b and b+1 ...
-            g.col_lo = u0 + 2; g.cskip0 = NOSKIP; g.cskipn = 0;          // ... x the 2 tile columns of b+1
-            launch_bulk(c, g, 2, nu - 4);
-            if ((rc = launch_pivot_phases(c, npad, ld, rate, next, mid, csT, rs, b0 + FW_B, 1, true)) != FW_OK) return rc;
-            // fused: everything outside the strips of b+1
-            g.nb = 2; g.half_r0 = u0; g.half_c0 = u0;
-            g.row_lo = 0; g.rskip0 = u0 + 2; g.rskipn = 2;
-            g.col_lo = 0; g.cskip0 = u0 + 2; g.cskipn = 2;
+            g.row_lo = 0; g.rskip0 = uL; g.rskipn = 2;
+            g.col_lo = 0; g.cskip0 = uL; g.cskipn = 2;
             launch_bulk(c, g, nu - 2, nu - 2);
-            b += 2;
         }
         CU(cudaGetLastError());
+        b = bn; gn = gnn; sbase ^= 2;
     }
+    c->cur = nullptr;
+    if (two) { CU(cudaEventRecord(c->ev_side, T)); CU(cudaStreamWaitEvent(S, c->ev_side, 0)); }
     return FW_OK;
 }
 
@@ -375,6 +422,7 @@ int solve_tiles(fw_ctx *c, int batch, int n, long long ld, long long stride, dou
 int solve_device_locked(fw_ctx *c, int n, long long ld, double *rate, int32_t *next, int32_t *mid,
                         int32_t *csT, int32_t *rs, bool validate) {
     int rc;
+    c->cur = nullptr;
     if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
     if (validate && (rc = validate_device(c, rate, next, ld, 0, 1, n)) != FW_OK) return rc;
     const bool paths = (mid != nullptr);
@@ -482,6 +530,14 @@ int fw_ctx_create(int device, fw_ctx **out) {
         delete c; return cuda_fail(e, "cudaStreamCreate");
     }
     c->stream = c->own_stream;
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, hi) != cudaSuccess) c->side_stream = nullptr;
+        cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming);
+        if (const char *e = getenv("FW_OVERLAP")) c->overlap = atoi(e) != 0;
+    }
     if ((e = cudaMalloc(&c->d_flag, sizeof(int))) != cudaSuccess) { delete c; return cuda_fail(e, "cudaMalloc"); }
     if ((e = cudaMallocHost(&c->h_flag, sizeof(int))) != cudaSuccess) { delete c; return cuda_fail(e, "cudaMallocHost"); }
     *out = c;
@@ -493,12 +549,15 @@ void fw_ctx_destroy(fw_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->edge_state) { fw_state_destroy(c->edge_state); c->edge_state = nullptr; }
-    for (int i = 0; i < 2; ++i) { c->Cp[i].release(); c->Rw[i].release(); c->NCp[i].release(); }
+    for (int i = 0; i < 4; ++i) { c->Cp[i].release(); c->Rw[i].release(); c->NCp[i].release(); }
     c->w_rate.release(); c->w_next.release(); c->w_mid.release(); c->w_csT.release(); c->w_rs.release();
     c->s_rate.release(); c->s_next.release(); c->s_mid.release(); c->s_csT.release(); c->s_rs.release();
     if (c->d_flag) cudaFree(c->d_flag);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
+    if (c->ev_main) cudaEventDestroy(c->ev_main);
+    if (c->ev_side) cudaEventDestroy(c->ev_side);
     delete c;
 }
 
@@ -1001,6 +1060,7 @@ int fw_shard_pivot(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld,
     if (b0 < row0 || b0 >= row0 + rows) return fail(FW_ERR_INVALID, "fw_shard_pivot: this shard does not own k-block b0");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
+    c->cur = nullptr;
     int rc;
     if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
     if ((rc = c->Cp[0].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
@@ -1042,6 +1102,7 @@ int fw_shard_update_ex(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t
         return fail(FW_ERR_INVALID, "fw_shard_update_ex: bad mode / row range");
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
+    c->cur = nullptr;
     int rc;
     if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
     if ((rc = c->Cp[0].ensure((size_t)rows * FW_B)) != FW_OK) return rc;

@@ -29,4 +29,4 @@ for n in sizes:
         print("  bulk ms per launch (every %d-th): " % q + " ".join(f"{v:.3f}" for v in spans[::q]))
     print(json.dumps({"n": n, "ms": round(best, 3), "relax_per_s": f"{n**3 / (best * 1e-3):.4e}",
                       "phase_ms": [round(m, 3) for m in ms], "phase_launches": cnt,
-                      "bulk_relax_per_s": f"{(n - 128) ** 2 * 128 * cnt[3] / (ms[3] * 1e-3 + 1e-12):.4e}"}))
+                      "bulk_relax_per_s": f"{(n // 128) * (n - 128) ** 2 * 128 / (ms[3] * 1e-3 + 1e-12):.4e}"}))
