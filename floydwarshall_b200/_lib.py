@@ -11,7 +11,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfwgpu.so")
+LIB_PATH = os.environ.get("FWGPU_LIB") or os.path.join(_HERE, "libfwgpu.so")   # FWGPU_LIB: experiment builds
 
 FW_OK = 0
 FW_ERR_INVALID = -1

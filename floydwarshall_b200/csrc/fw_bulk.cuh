@@ -55,6 +55,13 @@ struct BulkArgs {
 constexpr int BULK_TR = 64;   // tile rows
 constexpr int BULK_KC = 16;   // k-chunk
 constexpr int BULK_ST = 3;    // cp.async pipeline stages (one __syncthreads per chunk)
+#ifndef FW_BULK_UNROLL
+#define FW_BULK_UNROLL 2      // k steps per loop body of the bulk kernel (experiment knob)
+#endif
+constexpr int BULK_UNROLL = FW_BULK_UNROLL;
+#ifndef FW_BULK_ONELEVEL
+#define FW_BULK_ONELEVEL 0    // 1: no per-row candidate words; a candidate replays all 8 rows exactly
+#endif
 template <int CQ>
 constexpr size_t bulk_smem_bytes() {
     return sizeof(double) * BULK_ST * BULK_KC * (BULK_TR + 32 * CQ) + sizeof(int) * (16 * CQ) * 128;
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
             }
         };
         fetch(0, av, bv);
-#pragma unroll 2
+#pragma unroll BULK_UNROLL
         for (int kk = 0; kk < BULK_KC; ++kk) {
             double avn[8], bvn[NC];
             fetch((kk + 1 < BULK_KC) ? kk + 1 : kk, avn, bvn);
@@ -183,15 +190,23 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
 #pragma unroll
                 for (int c = 0; c < NC; ++c) hi[r][c] = __double2hiint(__fma_rd(av[r], bv[c], -o[r][c]));
             // two levels: accr[r] covers micro-tile row r, acc the whole step
+#if FW_BULK_ONELEVEL
+            const int acc = and_tree<8 * NC>(&hi[0][0]);
+#else
             int accr[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) accr[r] = and_tree<NC>(hi[r]);
             const int acc = and_tree<8>(accr);
+#endif
             if (__builtin_expect(__any_sync(0xffffffffu, acc >= 0), 0)) {
                 const int kloc = ch * BULK_KC + kk;   // step index relative to b0 (0..255)
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
+#if FW_BULK_ONELEVEL
+                    {
+#else
                     if (__any_sync(0xffffffffu, accr[r] >= 0)) {
+#endif
                         // exact path: one rounded multiply, strict compare (Algorithms.hs:55,61)
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
