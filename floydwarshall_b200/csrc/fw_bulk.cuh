@@ -59,8 +59,11 @@ constexpr int BULK_ST = 3;    // cp.async pipeline stages (one __syncthreads per
 #define FW_BULK_UNROLL 2      // k steps per loop body of the bulk kernel (experiment knob)
 #endif
 constexpr int BULK_UNROLL = FW_BULK_UNROLL;
-#ifndef FW_BULK_ONELEVEL
-#define FW_BULK_ONELEVEL 0    // 1: no per-row candidate words; a candidate replays all 8 rows exactly
+#ifndef FW_BULK_MINCTAS
+#define FW_BULK_MINCTAS 3      // resident CTAs/SM the 8x4 variant is compiled for (register cap 168)
+#endif
+#ifndef FW_BULK_PREFETCH
+#define FW_BULK_PREFETCH 1     // fetch the operands of step k+1 during step k
 #endif
 template <int CQ>
 constexpr size_t bulk_smem_bytes() {
@@ -76,7 +79,7 @@ __device__ __forceinline__ int and_tree(const int *h) {
 }
 
 template <int CQ>
-__global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArgs a) {
+__global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_kernel(BulkArgs a) {
     constexpr int TW = 32 * CQ;      // tile width (columns)
     constexpr int NC = 2 * CQ;       // columns per thread
     extern __shared__ __align__(16) unsigned char bulk_smem[];
@@ -178,11 +181,17 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
                 bx[cq * 2] = v.x; bx[cq * 2 + 1] = v.y;
             }
         };
+#if FW_BULK_PREFETCH
         fetch(0, av, bv);
+#endif
 #pragma unroll BULK_UNROLL
         for (int kk = 0; kk < BULK_KC; ++kk) {
+#if FW_BULK_PREFETCH
             double avn[8], bvn[NC];
             fetch((kk + 1 < BULK_KC) ? kk + 1 : kk, avn, bvn);
+#else
+            fetch(kk, av, bv);
+#endif
             // all DFMAs of the step first, then the integer reduction of their sign words
             int hi[8][NC];
 #pragma unroll
@@ -190,23 +199,15 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
 #pragma unroll
                 for (int c = 0; c < NC; ++c) hi[r][c] = __double2hiint(__fma_rd(av[r], bv[c], -o[r][c]));
             // two levels: accr[r] covers micro-tile row r, acc the whole step
-#if FW_BULK_ONELEVEL
-            const int acc = and_tree<8 * NC>(&hi[0][0]);
-#else
             int accr[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) accr[r] = and_tree<NC>(hi[r]);
             const int acc = and_tree<8>(accr);
-#endif
             if (__builtin_expect(__any_sync(0xffffffffu, acc >= 0), 0)) {
                 const int kloc = ch * BULK_KC + kk;   // step index relative to b0 (0..255)
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-#if FW_BULK_ONELEVEL
-                    {
-#else
                     if (__any_sync(0xffffffffu, accr[r] >= 0)) {
-#endif
                         // exact path: one rounded multiply, strict compare (Algorithms.hs:55,61)
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
@@ -220,10 +221,12 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? 3 : 2)) fw_bulk_kernel(BulkArg
                     }
                 }
             }
+#if FW_BULK_PREFETCH
 #pragma unroll
             for (int r = 0; r < 8; ++r) av[r] = avn[r];
 #pragma unroll
             for (int c = 0; c < NC; ++c) bv[c] = bvn[c];
+#endif
         }
         buf = (buf == BULK_ST - 1) ? 0 : buf + 1;
     }
