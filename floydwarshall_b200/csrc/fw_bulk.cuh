@@ -50,6 +50,10 @@ struct BulkArgs {
     // nb == 2: tiles in the strips of the FIRST block (tile rows [half_r0, half_r0+2) or tile columns
     // of the first block) already took its 128 steps in phase 2 and only run the second block's.
     int half_r0, half_c0;         // tile row / 64-column unit of the first block; huge if none
+    // 1-D grid of gx*gy CTAs, rasterised in column bands of `band` tile columns: a band's slice of the
+    // row-snapshot panels (band*TW columns x 256 steps x 8 B, a few MB) stays hot in L2 while the CTAs
+    // sweep all tile rows, instead of the whole 64 MB panel being re-streamed for every tile row.
+    int gx, gy, band;
 };
 
 constexpr int BULK_TR = 64;   // tile rows
@@ -95,7 +99,16 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
     const int tid = threadIdx.x;
     const int ty = tid >> 4, tx = tid & 15;
     constexpr int CU = TW / 64;             // 64-column units per tile column
-    int ti = a.row_lo + (int)blockIdx.y, tj = a.col_lo / CU + (int)blockIdx.x;
+    int bx, by;
+    {
+        const int lin = (int)blockIdx.x;
+        const int per_band = a.band * a.gy;
+        const int bi = lin / per_band, rem = lin - bi * per_band;
+        const int w = min(a.band, a.gx - bi * a.band);       // width of this (possibly last, narrower) band
+        by = rem / w;
+        bx = bi * a.band + (rem - by * w);
+    }
+    int ti = a.row_lo + by, tj = a.col_lo / CU + bx;
     if (ti >= a.rskip0) ti += a.rskipn;
     if (tj >= a.cskip0 / CU) tj += a.cskipn / CU;
     const int i0 = ti * BULK_TR, j0 = tj * TW;
@@ -141,8 +154,9 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
         const long long ro = (long long)(i0 + ty * 8 + r) * ld + j0 + tx * 2;
 #pragma unroll
         for (int cq = 0; cq < CQ; ++cq) {
-            o[r][cq * 2] = __ldg(a.rate + ro + cq * 32);
-            o[r][cq * 2 + 1] = __ldg(a.rate + ro + cq * 32 + 1);
+            // streamed once per launch: evict-first, so that the snapshot panels keep their L2 lines
+            o[r][cq * 2] = __ldcs(a.rate + ro + cq * 32);
+            o[r][cq * 2 + 1] = __ldcs(a.rate + ro + cq * 32 + 1);
         }
     }
     {   // the matrix diagonal crosses this tile: hold it as NaN (see fw_common.cuh)

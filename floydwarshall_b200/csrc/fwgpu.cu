@@ -160,6 +160,7 @@ struct fw_ctx {
     int *h_flag = nullptr;
     bool attrs_set = false;
     int bulk_cq = 2;       // fw_bulk_kernel tile width / 32 (2: 8x4 micro-tile, 4: 8x8); knob FW_BULK_CQ
+    int bulk_band = 64;    // tile columns per raster band of fw_bulk_kernel (L2 locality); knob FW_BULK_BAND
     // optional per-phase timing (CUDA events on the launching stream)
     bool profiling = false;
     struct Span { cudaEvent_t a, b; int phase; };
@@ -191,6 +192,7 @@ int set_kernel_attrs(fw_ctx *c) {
     CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     if (const char *e = getenv("FW_BULK_CQ")) c->bulk_cq = atoi(e) == 4 ? 4 : 2;
     if (const char *e = getenv("FW_FUSE_PAIRS")) c->fuse_pairs = atoi(e) != 0;
+    if (const char *e = getenv("FW_BULK_BAND")) c->bulk_band = atoi(e) > 0 ? atoi(e) : 64;
     c->attrs_set = true;
     return FW_OK;
 }
@@ -225,15 +227,19 @@ int grid_for(long long total, int sm_count) {
 }
 
 // Tile ranges are given in 64-row / 64-column units (see fw::BulkArgs); ncu = units of columns, nru = of rows.
-void launch_bulk(fw_ctx *c, const fw::BulkArgs &g, int ncu, int nru) {
+void launch_bulk(fw_ctx *c, fw::BulkArgs g, int ncu, int nru) {
     if (ncu <= 0 || nru <= 0) return;
     PhaseTimer pt(c, 3);
+    g.gy = nru;
+    g.band = c->bulk_band;
     if (c->bulk_cq == 4) {
-        const dim3 grid(ncu / 2, nru);
-        fw::fw_bulk_kernel<4><<<grid, 128, fw::bulk_smem_bytes<4>(), (c->cur ? c->cur : c->stream)>>>(g);
+        g.gx = ncu / 2;
+        if (g.band > g.gx) g.band = g.gx;
+        fw::fw_bulk_kernel<4><<<g.gx * g.gy, 128, fw::bulk_smem_bytes<4>(), (c->cur ? c->cur : c->stream)>>>(g);
     } else {
-        const dim3 grid(ncu, nru);
-        fw::fw_bulk_kernel<2><<<grid, 128, fw::bulk_smem_bytes<2>(), (c->cur ? c->cur : c->stream)>>>(g);
+        g.gx = ncu;
+        if (g.band > g.gx) g.band = g.gx;
+        fw::fw_bulk_kernel<2><<<g.gx * g.gy, 128, fw::bulk_smem_bytes<2>(), (c->cur ? c->cur : c->stream)>>>(g);
     }
     c->launches++;
 }
