@@ -69,10 +69,19 @@ constexpr int BULK_UNROLL = FW_BULK_UNROLL;
 #ifndef FW_BULK_PREFETCH
 #define FW_BULK_PREFETCH 1     // fetch the operands of step k+1 during step k
 #endif
+#ifndef FW_BULK_LATEVOTE
+#define FW_BULK_LATEVOTE 1     // vote on step k's sign words after step k+1's DFMAs (tools/loop_probe V7)
+#endif
 template <int CQ>
 constexpr size_t bulk_smem_bytes() {
     return sizeof(double) * BULK_ST * BULK_KC * (BULK_TR + 32 * CQ) + sizeof(int) * (16 * CQ) * 128;
 }
+
+#ifdef FW_BULK_STATS
+// experiment build only (make VARIANT=_stats EXTRA=-DFW_BULK_STATS): [0] warp-steps, [1] warp-steps that left
+// the fast path, [2] micro-tile rows replayed, [3] entries replaced.  Read with fw_debug_bulk_stats().
+__device__ unsigned long long fw_bulk_stats[4];
+#endif
 
 template <int N>
 __device__ __forceinline__ int and_tree(const int *h) {
@@ -195,6 +204,47 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
                 bx[cq * 2] = v.x; bx[cq * 2 + 1] = v.y;
             }
         };
+        // exact path for step `ks` of this chunk (operands re-read from shared memory: it is rare):
+        // one rounded multiply, strict compare (Algorithms.hs:55,61), rows selected by their sign words
+        auto vote_and_replay = [&](const int (&rw)[8], int ks) {
+            const int acc = and_tree<8>(rw);
+#ifdef FW_BULK_STATS
+            if ((tid & 31) == 0) atomicAdd(&fw_bulk_stats[0], 1ull);
+#endif
+            if (__builtin_expect(__any_sync(0xffffffffu, acc >= 0), 0)) {
+                const int kloc = ch * BULK_KC + ks;   // step index relative to b0 (0..255)
+#ifdef FW_BULK_STATS
+                if ((tid & 31) == 0) atomicAdd(&fw_bulk_stats[1], 1ull);
+#endif
+                double ax[8], bx[NC];
+                fetch(ks, ax, bx);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    if (__any_sync(0xffffffffu, rw[r] >= 0)) {
+#ifdef FW_BULK_STATS
+                        if ((tid & 31) == 0) atomicAdd(&fw_bulk_stats[2], 1ull);
+#endif
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            const double n = ax[r] * bx[c];
+                            if (o[r][c] < n) {
+#ifdef FW_BULK_STATS
+                                atomicAdd(&fw_bulk_stats[3], 1ull);
+#endif
+                                o[r][c] = n;
+                                Ms[r * NC + c][tid] = kloc;
+                                chg |= 1ull << (r * NC + c);
+                            }
+                        }
+                    }
+                }
+            }
+        };
+#if FW_BULK_LATEVOTE
+        int hprev[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) hprev[r] = -1;      // "no candidate": the vote of step -1 is a no-op
+#endif
 #if FW_BULK_PREFETCH
         fetch(0, av, bv);
 #endif
@@ -216,25 +266,17 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
             int accr[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) accr[r] = and_tree<NC>(hi[r]);
-            const int acc = and_tree<8>(accr);
-            if (__builtin_expect(__any_sync(0xffffffffu, acc >= 0), 0)) {
-                const int kloc = ch * BULK_KC + kk;   // step index relative to b0 (0..255)
+#if FW_BULK_LATEVOTE
+            // the second level and the vote run one step late, behind the next step's DFMAs: the row words of
+            // step kk-1 (hprev) are voted on here.  A replay of step kk-1 after the filter of step kk is
+            // still exact-order: the filter only PROVES "nothing fires", and it stays conservative when it
+            // saw entries that a later replay then raises (a smaller o can only add candidates).
+            vote_and_replay(hprev, kk - 1);
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    if (__any_sync(0xffffffffu, accr[r] >= 0)) {
-                        // exact path: one rounded multiply, strict compare (Algorithms.hs:55,61)
-#pragma unroll
-                        for (int c = 0; c < NC; ++c) {
-                            const double n = av[r] * bv[c];
-                            if (o[r][c] < n) {
-                                o[r][c] = n;
-                                Ms[r * NC + c][tid] = kloc;
-                                chg |= 1ull << (r * NC + c);
-                            }
-                        }
-                    }
-                }
-            }
+            for (int r = 0; r < 8; ++r) hprev[r] = accr[r];
+#else
+            vote_and_replay(accr, kk);
+#endif
 #if FW_BULK_PREFETCH
 #pragma unroll
             for (int r = 0; r < 8; ++r) av[r] = avn[r];
@@ -242,6 +284,9 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
             for (int c = 0; c < NC; ++c) bv[c] = bvn[c];
 #endif
         }
+#if FW_BULK_LATEVOTE
+        vote_and_replay(hprev, BULK_KC - 1);   // the chunk's last step, before its buffer can be recycled
+#endif
         buf = (buf == BULK_ST - 1) ? 0 : buf + 1;
     }
 

@@ -1169,3 +1169,16 @@ int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld
 }
 
 }  // extern "C"
+
+#ifdef FW_BULK_STATS
+// experiment build only: read (and optionally clear) the bulk kernel's fast-path counters
+extern "C" int fw_debug_bulk_stats(unsigned long long out[4], int reset) {
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(out, fw::fw_bulk_stats, 4 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    if (reset) {
+        unsigned long long z[4] = {0, 0, 0, 0};
+        if (cudaMemcpyToSymbol(fw::fw_bulk_stats, z, sizeof(z)) != cudaSuccess) return -1;
+    }
+    return 0;
+}
+#endif
