@@ -69,18 +69,44 @@ constexpr int BULK_UNROLL = FW_BULK_UNROLL;
 #ifndef FW_BULK_PREFETCH
 #define FW_BULK_PREFETCH 1     // fetch the operands of step k+1 during step k
 #endif
+#ifndef FW_BULK_TMA
+#define FW_BULK_TMA 0          // 1: panels staged by cp.async.bulk (TMA, 1-D) + mbarriers instead of cp.async (LDGSTS)
+#endif
 #ifndef FW_BULK_LATEVOTE
-#define FW_BULK_LATEVOTE 1     // vote on step k's sign words after step k+1's DFMAs (tools/loop_probe V7)
+#define FW_BULK_LATEVOTE 0     // 1: vote on step k's sign words after step k+1's DFMAs (loop_probe V7: +5 % in isolation, -3.5 % in the solve)
 #endif
 template <int CQ>
 constexpr size_t bulk_smem_bytes() {
-    return sizeof(double) * BULK_ST * BULK_KC * (BULK_TR + 32 * CQ) + sizeof(int) * (16 * CQ) * 128;
+    return sizeof(double) * BULK_ST * BULK_KC * (BULK_TR + 32 * CQ) + sizeof(int) * (16 * CQ) * 128 +
+           (FW_BULK_TMA ? 2 * BULK_ST * sizeof(unsigned long long) : 0);
 }
 
 #ifdef FW_BULK_STATS
 // experiment build only (make VARIANT=_stats EXTRA=-DFW_BULK_STATS): [0] warp-steps, [1] warp-steps that left
 // the fast path, [2] micro-tile rows replayed, [3] entries replaced.  Read with fw_debug_bulk_stats().
 __device__ unsigned long long fw_bulk_stats[4];
+#endif
+
+#if FW_BULK_TMA
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @!p bra W;\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 #endif
 
 template <int N>
@@ -127,6 +153,40 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
         kstart = FW_B;
     const long long ld = a.ld;
 
+#if FW_BULK_TMA
+    // TMA staging: lane l of warp 0 owns one 1-D bulk copy per chunk -- l < 16: row l of the A chunk
+    // (64 doubles of CpT), l >= 16: row l-16 of the B chunk (TW doubles of Rw).  full[s] completes when the
+    // 16 + 16 rows of stage s have landed (expect_tx), empty[s] when all four warps are done reading it.
+    constexpr unsigned bufA = BULK_KC * BULK_TR * 8, bufB = BULK_KC * TW * 8;   // bytes per stage
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(
+        bulk_smem + sizeof(double) * BULK_ST * BULK_KC * (BULK_TR + TW) + sizeof(int) * (8 * NC) * 128);
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(bars);          // full[s] = bar0 + 8 s, empty[s] = bar0 + 8 (ST + s)
+    const int lane = tid & 31;
+    const bool producer = tid < 32;
+    if (tid == 0) {
+#pragma unroll
+        for (int st = 0; st < BULK_ST; ++st) { mbar_init(bar0 + 8 * st, 1); mbar_init(bar0 + 8 * (BULK_ST + st), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const bool isA = lane < 16;
+    const int prow = lane & 15;
+    const long long poff = isA ? ((long long)prow * a.ldc + i0) : ((long long)prow * a.ldw + j0);
+    const unsigned pdst = isA ? (unsigned)__cvta_generic_to_shared(&As[0][prow][0]) : (unsigned)__cvta_generic_to_shared(&Bs[0][prow][0]);
+    auto load_chunk = [&](int c, int stage) {       // warp 0 only
+        const int set = c >> 3, kk0 = (c & 7) * BULK_KC;
+        const unsigned full = bar0 + 8 * stage;
+        if (lane == 0) mbar_expect_tx(full, bufA + bufB);
+        __syncwarp();
+        const double *src = isA ? a.CpT[set] + ((long long)kk0 * a.ldc + poff) : a.Rw[set] + ((long long)kk0 * a.ldw + poff);
+        bulk_g2s(pdst + stage * (isA ? bufA : bufB), src, isA ? BULK_TR * 8 : TW * 8, full);
+    };
+    const int ch0 = kstart / BULK_KC, ch1 = a.nb * (FW_B / BULK_KC);
+    if (producer) {
+        load_chunk(ch0, 0);
+        load_chunk(ch0 + 1, 1);
+    }
+#else
     // cp.async sources/destinations of this thread, computed once: piece p = tid + 128*t covers
     // A: row kk = (tid>>5) + 4t, 16 bytes at column (tid&31)*2;  B: likewise with TW/2 pieces per row.
     // 32-bit element offsets of this thread's first piece inside a panel (panels are < 2^31 elements)
@@ -156,6 +216,8 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
     load_chunk(ch0 + 1, 1);
     cp_async_commit();
 
+#endif
+
     double o[8][NC];
     unsigned long long chg = 0;   // bit e set <=> entry e of this thread was replaced (Ms[e][tid] valid)
 #pragma unroll
@@ -182,6 +244,15 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
     static_assert(BULK_ST == 3, "buffer rotation below assumes 3 stages");
     int buf = 0;
     for (int ch = ch0; ch < ch1; ++ch) {
+#if FW_BULK_TMA
+        const int it = ch - ch0;                         // chunk it uses stage it % 3 in its (it / 3)-th round
+        if (producer && ch + 2 < ch1) {
+            const int rs = buf == 0 ? 2 : buf - 1;       // (buf + 2) % 3 == the stage chunk it-1 used
+            if (it >= 1) mbar_wait(bar0 + 8 * (BULK_ST + rs), ((it - 1) / BULK_ST) & 1);   // all warps done with it
+            load_chunk(ch + 2, rs);
+        }
+        mbar_wait(bar0 + 8 * buf, (it / BULK_ST) & 1);   // chunk ch has landed
+#else
         // chunk ch has landed once at most one younger group is still in flight
         if (ch + 1 < ch1) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();   // (a) chunk ch visible to all; (b) everyone is done with chunk ch-1's buffer
@@ -189,6 +260,7 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
             load_chunk(ch + 2, buf == 0 ? 2 : buf - 1);   // (buf + 2) % 3 == the buffer chunk ch-1 used
             cp_async_commit();
         }
+#endif
         // operands of step kk are fetched one step ahead so that their shared-memory latency
         // hides behind the previous step's DFMAs and vote
         double av[8], bv[NC];
@@ -286,6 +358,10 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
         }
 #if FW_BULK_LATEVOTE
         vote_and_replay(hprev, BULK_KC - 1);   // the chunk's last step, before its buffer can be recycled
+#endif
+#if FW_BULK_TMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar0 + 8 * (BULK_ST + buf));   // this warp is done with the stage
 #endif
         buf = (buf == BULK_ST - 1) ? 0 : buf + 1;
     }
