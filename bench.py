@@ -365,6 +365,12 @@ def run_ours(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: native libraries write banners to fd 1 directly (NCCL prints
+    # "NCCL version ..." there), so fd 1 is pointed at stderr and Python's stdout keeps the real one.
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_out, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args)
     else:

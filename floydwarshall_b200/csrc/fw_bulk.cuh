@@ -230,14 +230,15 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
             o[r][cq * 2 + 1] = __ldcs(a.rate + ro + cq * 32 + 1);
         }
     }
-    {   // the matrix diagonal crosses this tile: hold it as NaN (see fw_common.cuh)
+    {   // the matrix diagonal crosses this tile: hold it as +inf -- o < n is false for every n, it is never
+        // written back (chg stays clear), and fma(a, b, -inf) = -inf keeps the filter on its fast path
         const int gi0 = a.row0 + i0;
         if (gi0 + BULK_TR > j0 && gi0 < j0 + TW) {
 #pragma unroll
             for (int r = 0; r < 8; ++r)
 #pragma unroll
                 for (int c = 0; c < NC; ++c)
-                    if (gi0 + ty * 8 + r == j0 + (c >> 1) * 32 + tx * 2 + (c & 1)) o[r][c] = qnan();
+                    if (gi0 + ty * 8 + r == j0 + (c >> 1) * 32 + tx * 2 + (c & 1)) o[r][c] = pinf();
         }
     }
 

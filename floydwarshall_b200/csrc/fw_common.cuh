@@ -9,13 +9,18 @@
 // Two facts shape every kernel here:
 //  * Step k writes neither row k nor column k, so in-place == the reference's
 //    generation-per-k form.
-//  * All three skip rules fall out of ONE trick: the diagonal is held as NaN
-//    on chip.  NaN < n is false (j == i never replaced), and R[k][k] = NaN
-//    makes every product of step k with i == k or j == k a NaN, for which
-//    o < NaN is false.  The diagonal is never a legitimate factor (i != k for
-//    R[i][k], j != k for R[k][j]), so no other product changes.  Padding rows
-//    and columns (n not a multiple of the tile) are NaN for the same reason.
-//    The trick is exact for every IEEE input, not just in-domain ones.
+//  * The three skip rules (i != k, j != k, j != i) need no branches:
+//      - an entry that must never be replaced (the diagonal, padding) is held on
+//        chip as NaN (tile kernel) or +inf (bulk kernel, so that the DFMA filter
+//        stays quiet): o < n is false for every n;
+//      - the pivot R[k][k] is held as NaN inside the tile kernel and exported to
+//        the panel kernels as 0.0: every product of step k with i == k or j == k
+//        is then NaN or 0, and neither beats an entry >= 0.  The diagonal is never
+//        a legitimate factor (i != k for R[i][k], j != k for R[k][j]), so no other
+//        product changes.  NaN is exact for every IEEE input; 0.0 is exact on the
+//        documented domain (entries >= 0, NaN and +inf tolerated; include/fwgpu.h),
+//        which fw_validate_kernel enforces before any kernel runs.
+//    Padding rows and columns (n not a multiple of the tile) are NaN in memory.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -27,6 +32,7 @@
 namespace fw {
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+__device__ __forceinline__ double pinf() { return __longlong_as_double(0x7ff0000000000000LL); }
 
 // one relaxation on register state; returns whether it fired
 __device__ __forceinline__ bool relax(double &o, double n) {

@@ -14,7 +14,10 @@
 // A job is spread over 16 lanes x 8 elements; the pivot element of step kk is
 // broadcast with warp shuffles, the factor row comes from a swizzled shared
 // copy of the B x B snapshot matrix (conflict-free LDS.128).  The diagonal of
-// that matrix is NaN, which is what makes element kk skip itself at step kk.
+// that matrix is 0.0 (fw_tile.cuh publishes "never a factor" entries as zero), which
+// is what makes element kk skip itself at step kk: s * 0 never beats an entry >= 0.
+// Every step runs the bulk kernel's one-DFMA filter first and the exact
+// mul / compare / select only when some lane of the warp has a candidate.
 // 512 threads = 32 jobs per CTA pass; persistent CTAs stride over the jobs.
 #pragma once
 #include "fw_common.cuh"
@@ -88,21 +91,29 @@ __global__ void __launch_bounds__(512, 1) fw_colpanel_kernel(PanelArgs a) {
             for (int c = 0; c < 8; ++c) {
                 const int kk = lt * 8 + c;
                 const double s = __shfl_sync(0xffffffffu, y[c], lt, 16);
-                const int snx = __shfl_sync(0xffffffffu, nx[c], lt, 16);
                 if (l == lt) {
-                    cs[c] = s; ncs[c] = snx;
+                    cs[c] = s; ncs[c] = nx[c];
                     if (PATHS) mcs[c] = md[c];
                 }
                 const double2 *fr = reinterpret_cast<const double2 *>(Fs + kk * PANEL_FP) + l;
                 double f[8];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { double2 v = fr[q * 16]; f[q * 2] = v.x; f[q * 2 + 1] = v.y; }
+                // filter (fw_bulk.cuh): a set sign bit of fma_rd(s, f, -y) proves y < RN(s*f) is false
+                int h[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const double n = s * f[e];
-                    if (y[e] < n) {
-                        y[e] = n; nx[e] = snx;
-                        if (PATHS) md[e] = b0 + kk;
+                for (int e = 0; e < 8; ++e) h[e] = __double2hiint(__fma_rd(s, f[e], -y[e]));
+                const int acc = ((h[0] & h[1] & h[2]) & (h[3] & h[4] & h[5])) & (h[6] & h[7]);
+                if (__any_sync(0xffffffffu, acc >= 0)) {
+                    // exact path: one rounded multiply, strict compare (Algorithms.hs:55,61)
+                    const int snx = __shfl_sync(0xffffffffu, nx[c], lt, 16);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const double n = s * f[e];
+                        if (y[e] < n) {
+                            y[e] = n; nx[e] = snx;
+                            if (PATHS) md[e] = b0 + kk;
+                        }
                     }
                 }
             }
@@ -172,10 +183,16 @@ __global__ void __launch_bounds__(512, 1) fw_rowpanel_kernel(PanelArgs a) {
                 double f[8];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { double2 v = fr[q * 16]; f[q * 2] = v.x; f[q * 2 + 1] = v.y; }
+                int h[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const double n = f[e] * s;
-                    if (x[e] < n) { x[e] = n; m[e] = kk; }
+                for (int e = 0; e < 8; ++e) h[e] = __double2hiint(__fma_rd(f[e], s, -x[e]));
+                const int acc = ((h[0] & h[1] & h[2]) & (h[3] & h[4] & h[5])) & (h[6] & h[7]);
+                if (__any_sync(0xffffffffu, acc >= 0)) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const double n = f[e] * s;
+                        if (x[e] < n) { x[e] = n; m[e] = kk; }
+                    }
                 }
             }
         }

@@ -105,12 +105,16 @@ __global__ void __launch_bounds__(512, 1) fw_tile_kernel(TileArgs a) {
                 const double *rb = rowbuf + buf * 128;
                 // snapshots for the other phases (diag mode only)
                 if (a.Cp != nullptr) {
+                    // The pivot itself (held as NaN in here, see fw_common.cuh) is EXPORTED as 0.0: the panel
+                    // kernels put the DFMA filter in front of their exact path, which a NaN factor would
+                    // defeat, and a zero factor skips i == k / j == k just as well for entries >= 0
+                    // (s * 0 is 0 or NaN, never larger) -- the domain fw_validate_kernel enforces.
                     if (tid < 128) {
-                        a.Cp[(long long)k * a.ldc + a.r0 + tid] = cb[tid];
+                        a.Cp[(long long)k * a.ldc + a.r0 + tid] = (tid == k) ? 0.0 : cb[tid];
                         a.NCp[(long long)(a.r0 + tid) * FW_B + k] = NXs[tid * TILE_NXP + k];
                     } else if (tid < 256) {
                         const int j = tid - 128;
-                        a.Rw[(long long)k * a.ldw + a.b0 + j] = rb[swz128(j)];
+                        a.Rw[(long long)k * a.ldw + a.b0 + j] = (j == k) ? 0.0 : rb[swz128(j)];
                     }
                 }
                 if (PATHS) {

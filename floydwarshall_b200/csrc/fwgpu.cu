@@ -149,7 +149,8 @@ struct fw_ctx {
     // snapshot panels
     DevBuf<double> Cp[4], Rw[4];   // panel sets: k-blocks go in pairs, and the next pair is factored ahead
     DevBuf<int32_t> NCp[4];
-    bool fuse_pairs = true;        // knob FW_FUSE_PAIRS=0 turns pairing off
+    bool fuse_pairs = true;        // knob FW_FUSE_PAIRS=0 turns pairing off, =2 forces it for every size
+    bool fuse_forced = false;
     // padded working copy (n not a multiple of FW_B) and host-API staging
     DevBuf<double> w_rate;
     DevBuf<int32_t> w_next, w_mid, w_csT, w_rs;
@@ -191,7 +192,7 @@ int set_kernel_attrs(fw_ctx *c) {
                             (int)fw::bulk_smem_bytes<4>()));
     CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     if (const char *e = getenv("FW_BULK_CQ")) c->bulk_cq = atoi(e) == 4 ? 4 : 2;
-    if (const char *e = getenv("FW_FUSE_PAIRS")) c->fuse_pairs = atoi(e) != 0;
+    if (const char *e = getenv("FW_FUSE_PAIRS")) { c->fuse_pairs = atoi(e) != 0; c->fuse_forced = atoi(e) == 2; }
     if (const char *e = getenv("FW_BULK_BAND")) c->bulk_band = atoi(e) > 0 ? atoi(e) : 64;
     c->attrs_set = true;
     return FW_OK;
@@ -326,7 +327,9 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
     }
     const int nblk = npad / FW_B;
     const int nu = npad / 64;                 // 64-row / 64-column units
-    const int gsz = c->fuse_pairs ? 2 : 1;
+    // pairing splits every bulk launch in three; below ~48 k-blocks the extra launches cost more than the
+    // second tile load saves (N=1024: 2.26 ms unpaired vs 2.50 ms paired; N=8192: 90.5 vs 87.4 ms)
+    const int gsz = (c->fuse_pairs && (nblk >= 48 || c->fuse_forced)) ? 2 : 1;
     cudaStream_t S = c->stream;
     cudaStream_t T = (c->overlap && c->side_stream) ? c->side_stream : c->stream;
     const bool two = (T != S);

@@ -160,3 +160,23 @@ def test_device_resident_api(ctx):
     ctx.set_stream(None)
     assert ctx.last_launches > 0
     assert_same(dense.DenseResult(rt.cpu().numpy(), xt.cpu().numpy()), ref)
+
+
+@pytest.mark.parametrize("knobs", [{"FW_FUSE_PAIRS": "2"}, {"FW_FUSE_PAIRS": "0"},
+                                   {"FW_FUSE_PAIRS": "2", "FW_OVERLAP": "0"},
+                                   {"FW_FUSE_PAIRS": "2", "FW_BULK_BAND": "3"}])
+@pytest.mark.parametrize("E,C", [(24, 16), (45, 16), (70, 10)])
+def test_schedule_variants(monkeypatch, E, C, knobs):
+    """n = 384, 720, 700: every schedule the large solves use (k-blocks in pairs, which by default
+    starts at 48 k-blocks; side-stream look-ahead; raster bands) must give the reference's bits.
+    The knobs are read when a context first launches, so each case takes a fresh context."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    c = _lib.Context(0)
+    try:
+        rate, nxt = graphs.exchange_graph(E, C, seed=3 * E + C, density=0.6)
+        ref = O.solve_dense(rate, nxt, paths=True, threads=0)
+        assert_same(dense.solve(rate, nxt, paths=True, ctx=c), ref, paths=True)
+        assert_same(dense.solve(rate, nxt, paths=False, ctx=c), ref)
+    finally:
+        c.close()
