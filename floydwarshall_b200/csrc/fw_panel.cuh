@@ -46,9 +46,20 @@ struct PanelArgs {
 
 constexpr int PANEL_FP = 130;  // shared pitch (doubles): 16-byte aligned rows, 4-way max conflict on transposed fill
 constexpr size_t panel_smem_bytes() { return (size_t)128 * PANEL_FP * 8; }
+// Jobs per half-warp.  A step is one dependent chain (shuffle -> 8 DFMA -> sign words -> vote), about 150
+// cycles long, and a 512-thread CTA has only 4 warps per SM sub-partition to hide it: with one job per
+// half-warp the kernels ran at a quarter of their issue rate.  NJ independent jobs per half-warp share the
+// factor loads and interleave their chains.  Measured (N=16384, per launch): NJ=2 is 20 % faster once there
+// are enough jobs to fill every SM twice over, and slower below that (N=4096: 53 vs 35 us) -- panel_nj().
+__host__ __device__ constexpr int panel_nj(int jobs, int sm_count) { return jobs >= 64 * sm_count ? 2 : 1; }
 
-template <bool PATHS>
+__device__ __forceinline__ int and8(const int (&h)[8]) {
+    return ((h[0] & h[1] & h[2]) & (h[3] & h[4] & h[5])) & (h[6] & h[7]);
+}
+
+template <bool PATHS, int NJ>
 __global__ void __launch_bounds__(512, 1) fw_colpanel_kernel(PanelArgs a) {
+    constexpr int PANEL_JOBS = 32 * NJ;   // jobs per CTA pass
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *Fs = reinterpret_cast<double *>(smem_raw);
     const int tid = threadIdx.x;
@@ -62,89 +73,102 @@ __global__ void __launch_bounds__(512, 1) fw_colpanel_kernel(PanelArgs a) {
 
     const int job = tid >> 4, l = tid & 15;
     const int nrows = a.rows - (a.skip_r0 < a.rows ? a.skipn : 0);
-    for (int g = blockIdx.x; g * 32 < nrows; g += gridDim.x) {
-        const int rp = g * 32 + job;
-        const int i = rp < a.skip_r0 ? rp : rp + a.skipn;   // local row, skipping the k-block rows
-        const long long off = (long long)i * a.ld + b0 + l * 8;
-        double y[8], cs[8];
-        int nx[8], ncs[8], md[8], mcs[8];
-        {
-            const double2 *p = reinterpret_cast<const double2 *>(a.rate + off);
+    for (int g = blockIdx.x; g * PANEL_JOBS < nrows; g += gridDim.x) {
+        long long off[NJ];
+        int irow[NJ];
+        double y[NJ][8];
+        int nx[NJ][8], md[NJ][8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { double2 v = p[q]; y[q * 2] = v.x; y[q * 2 + 1] = v.y; }
-            const int4 *pn = reinterpret_cast<const int4 *>(a.next + off);
+        for (int u = 0; u < NJ; ++u) {
+            const int rp = g * PANEL_JOBS + job * NJ + u;
+            irow[u] = rp < a.skip_r0 ? rp : rp + a.skipn;   // local row, skipping the k-block rows
+            off[u] = (long long)irow[u] * a.ld + b0 + l * 8;
+            const double2 *p = reinterpret_cast<const double2 *>(a.rate + off[u]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { double2 v = p[q]; y[u][q * 2] = v.x; y[u][q * 2 + 1] = v.y; }
+            const int4 *pn = reinterpret_cast<const int4 *>(a.next + off[u]);
             int4 n0 = pn[0], n1 = pn[1];
-            nx[0] = n0.x; nx[1] = n0.y; nx[2] = n0.z; nx[3] = n0.w;
-            nx[4] = n1.x; nx[5] = n1.y; nx[6] = n1.z; nx[7] = n1.w;
+            nx[u][0] = n0.x; nx[u][1] = n0.y; nx[u][2] = n0.z; nx[u][3] = n0.w;
+            nx[u][4] = n1.x; nx[u][5] = n1.y; nx[u][6] = n1.z; nx[u][7] = n1.w;
             if (PATHS) {
-                const int4 *pm = reinterpret_cast<const int4 *>(a.mid + off);
+                const int4 *pm = reinterpret_cast<const int4 *>(a.mid + off[u]);
                 int4 m0 = pm[0], m1 = pm[1];
-                md[0] = m0.x; md[1] = m0.y; md[2] = m0.z; md[3] = m0.w;
-                md[4] = m1.x; md[5] = m1.y; md[6] = m1.z; md[7] = m1.w;
+                md[u][0] = m0.x; md[u][1] = m0.y; md[u][2] = m0.z; md[u][3] = m0.w;
+                md[u][4] = m1.x; md[u][5] = m1.y; md[u][6] = m1.z; md[u][7] = m1.w;
             }
         }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { cs[c] = 0.0; ncs[c] = -1; mcs[c] = -1; }
 
         for (int lt = 0; lt < 16; ++lt) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int kk = lt * 8 + c;
-                const double s = __shfl_sync(0xffffffffu, y[c], lt, 16);
+                double s[NJ];
+#pragma unroll
+                for (int u = 0; u < NJ; ++u) s[u] = __shfl_sync(0xffffffffu, y[u][c], lt, 16);
                 if (l == lt) {
-                    cs[c] = s; ncs[c] = nx[c];
-                    if (PATHS) mcs[c] = md[c];
+                    // the step-kk snapshots of column b0+kk, written as they are taken
+#pragma unroll
+                    for (int u = 0; u < NJ; ++u) {
+                        a.Cp[(long long)kk * a.ldc + irow[u]] = s[u];
+                        a.NCp[(long long)irow[u] * FW_B + kk] = nx[u][c];
+                        if (PATHS) a.csT[off[u] + c] = md[u][c];
+                    }
                 }
                 const double2 *fr = reinterpret_cast<const double2 *>(Fs + kk * PANEL_FP) + l;
                 double f[8];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { double2 v = fr[q * 16]; f[q * 2] = v.x; f[q * 2 + 1] = v.y; }
                 // filter (fw_bulk.cuh): a set sign bit of fma_rd(s, f, -y) proves y < RN(s*f) is false
-                int h[8];
+                int hu[NJ];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) h[e] = __double2hiint(__fma_rd(s, f[e], -y[e]));
-                const int acc = ((h[0] & h[1] & h[2]) & (h[3] & h[4] & h[5])) & (h[6] & h[7]);
+                for (int u = 0; u < NJ; ++u) {
+                    int h[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) h[e] = __double2hiint(__fma_rd(s[u], f[e], -y[u][e]));
+                    hu[u] = and8(h);
+                }
+                int acc = hu[0];
+#pragma unroll
+                for (int u = 1; u < NJ; ++u) acc &= hu[u];
                 if (__any_sync(0xffffffffu, acc >= 0)) {
-                    // exact path: one rounded multiply, strict compare (Algorithms.hs:55,61)
-                    const int snx = __shfl_sync(0xffffffffu, nx[c], lt, 16);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const double n = s * f[e];
-                        if (y[e] < n) {
-                            y[e] = n; nx[e] = snx;
-                            if (PATHS) md[e] = b0 + kk;
+                    for (int u = 0; u < NJ; ++u) {
+                        if (__any_sync(0xffffffffu, hu[u] >= 0)) {
+                            // exact path: one rounded multiply, strict compare (Algorithms.hs:55,61)
+                            const int snx = __shfl_sync(0xffffffffu, nx[u][c], lt, 16);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const double n = s[u] * f[e];
+                                if (y[u][e] < n) {
+                                    y[u][e] = n; nx[u][e] = snx;
+                                    if (PATHS) md[u][e] = b0 + kk;
+                                }
+                            }
                         }
                     }
                 }
             }
         }
-        {
-            double2 *p = reinterpret_cast<double2 *>(a.rate + off);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) p[q] = make_double2(y[q * 2], y[q * 2 + 1]);
-            int4 *pn = reinterpret_cast<int4 *>(a.next + off);
-            pn[0] = make_int4(nx[0], nx[1], nx[2], nx[3]);
-            pn[1] = make_int4(nx[4], nx[5], nx[6], nx[7]);
-            const long long poff = (long long)i * FW_B + l * 8;
+        for (int u = 0; u < NJ; ++u) {
+            double2 *p = reinterpret_cast<double2 *>(a.rate + off[u]);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) a.Cp[(long long)(l * 8 + c) * a.ldc + i] = cs[c];
-            int4 *pnc = reinterpret_cast<int4 *>(a.NCp + poff);
-            pnc[0] = make_int4(ncs[0], ncs[1], ncs[2], ncs[3]);
-            pnc[1] = make_int4(ncs[4], ncs[5], ncs[6], ncs[7]);
+            for (int q = 0; q < 4; ++q) p[q] = make_double2(y[u][q * 2], y[u][q * 2 + 1]);
+            int4 *pn = reinterpret_cast<int4 *>(a.next + off[u]);
+            pn[0] = make_int4(nx[u][0], nx[u][1], nx[u][2], nx[u][3]);
+            pn[1] = make_int4(nx[u][4], nx[u][5], nx[u][6], nx[u][7]);
             if (PATHS) {
-                int4 *pm = reinterpret_cast<int4 *>(a.mid + off);
-                pm[0] = make_int4(md[0], md[1], md[2], md[3]);
-                pm[1] = make_int4(md[4], md[5], md[6], md[7]);
-                int4 *pcs = reinterpret_cast<int4 *>(a.csT + off);
-                pcs[0] = make_int4(mcs[0], mcs[1], mcs[2], mcs[3]);
-                pcs[1] = make_int4(mcs[4], mcs[5], mcs[6], mcs[7]);
+                int4 *pm = reinterpret_cast<int4 *>(a.mid + off[u]);
+                pm[0] = make_int4(md[u][0], md[u][1], md[u][2], md[u][3]);
+                pm[1] = make_int4(md[u][4], md[u][5], md[u][6], md[u][7]);
             }
         }
     }
 }
 
-template <bool PATHS>
+template <bool PATHS, int NJ>
 __global__ void __launch_bounds__(512, 1) fw_rowpanel_kernel(PanelArgs a) {
+    constexpr int PANEL_JOBS = 32 * NJ;   // jobs per CTA pass
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *Fs = reinterpret_cast<double *>(smem_raw);
     const int tid = threadIdx.x;
@@ -158,55 +182,76 @@ __global__ void __launch_bounds__(512, 1) fw_rowpanel_kernel(PanelArgs a) {
 
     const int job = tid >> 4, l = tid & 15;
     const int ncols = a.npad - FW_B;
-    for (int g = blockIdx.x; g * 32 < ncols; g += gridDim.x) {
-        const int jp = g * 32 + job;
+    for (int g = blockIdx.x; g * PANEL_JOBS < ncols; g += gridDim.x) {
+        // NJ adjacent columns per half-warp (never straddling the k-block: b0 and NJ divide 128)
+        const int jp = g * PANEL_JOBS + job * NJ;
         const int j = jp < b0 ? jp : jp + FW_B;
-        const long long off = (long long)(a.blk_r0 + l * 8) * a.ld + j;  // + c*ld
-        double x[8], snap[8];
-        int m[8], mo[8], msnap[8];
+        const long long off = (long long)(a.blk_r0 + l * 8) * a.ld + j;  // + c*ld + u
+        double x[NJ][8];
+        int m[NJ][8], mo[NJ][8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            x[c] = a.rate[off + (long long)c * a.ld];
-            m[c] = -1; snap[c] = 0.0; msnap[c] = -1;
-            if (PATHS) mo[c] = a.mid[off + (long long)c * a.ld];
-        }
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int u = 0; u < NJ; ++u) {
+                x[u][c] = a.rate[off + (long long)c * a.ld + u];
+                m[u][c] = -1;
+                if (PATHS) mo[u][c] = a.mid[off + (long long)c * a.ld + u];
+            }
         for (int lt = 0; lt < 16; ++lt) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int kk = lt * 8 + c;
-                const double s = __shfl_sync(0xffffffffu, x[c], lt, 16);
+                double s[NJ];
+#pragma unroll
+                for (int u = 0; u < NJ; ++u) s[u] = __shfl_sync(0xffffffffu, x[u][c], lt, 16);
                 if (l == lt) {
-                    snap[c] = s;
-                    if (PATHS) msnap[c] = (m[c] >= 0) ? b0 + m[c] : mo[c];
+                    // the step-kk snapshot of row b0+kk, written as it is taken
+#pragma unroll
+                    for (int u = 0; u < NJ; ++u) {
+                        a.Rw[(long long)kk * a.ldw + j + u] = s[u];
+                        if (PATHS) a.rs[off + (long long)c * a.ld + u] = (m[u][c] >= 0) ? b0 + m[u][c] : mo[u][c];
+                    }
                 }
                 const double2 *fr = reinterpret_cast<const double2 *>(Fs + kk * PANEL_FP) + l;
                 double f[8];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) { double2 v = fr[q * 16]; f[q * 2] = v.x; f[q * 2 + 1] = v.y; }
-                int h[8];
+                int hu[NJ];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) h[e] = __double2hiint(__fma_rd(f[e], s, -x[e]));
-                const int acc = ((h[0] & h[1] & h[2]) & (h[3] & h[4] & h[5])) & (h[6] & h[7]);
+                for (int u = 0; u < NJ; ++u) {
+                    int h[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) h[e] = __double2hiint(__fma_rd(f[e], s[u], -x[u][e]));
+                    hu[u] = and8(h);
+                }
+                int acc = hu[0];
+#pragma unroll
+                for (int u = 1; u < NJ; ++u) acc &= hu[u];
                 if (__any_sync(0xffffffffu, acc >= 0)) {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const double n = f[e] * s;
-                        if (x[e] < n) { x[e] = n; m[e] = kk; }
+                    for (int u = 0; u < NJ; ++u) {
+                        if (__any_sync(0xffffffffu, hu[u] >= 0)) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) {
+                                const double n = f[e] * s[u];
+                                if (x[u][e] < n) { x[u][e] = n; m[u][e] = kk; }
+                            }
+                        }
                     }
                 }
             }
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const long long o = off + (long long)c * a.ld;
-            if (m[c] >= 0) {
-                a.rate[o] = x[c];
-                a.next[o] = a.NCp[(long long)(a.blk_r0 + l * 8 + c) * FW_B + m[c]];
-                if (PATHS) a.mid[o] = b0 + m[c];
+        for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int u = 0; u < NJ; ++u) {
+                const long long o = off + (long long)c * a.ld + u;
+                if (m[u][c] >= 0) {
+                    a.rate[o] = x[u][c];
+                    a.next[o] = a.NCp[(long long)(a.blk_r0 + l * 8 + c) * FW_B + m[u][c]];
+                    if (PATHS) a.mid[o] = b0 + m[u][c];
+                }
             }
-            a.Rw[(long long)(l * 8 + c) * a.ldw + j] = snap[c];
-            if (PATHS) a.rs[o] = msnap[c];
-        }
     }
 }
 

@@ -177,13 +177,21 @@ int set_kernel_attrs(fw_ctx *c) {
                             (int)fw::tile_smem_bytes(false)));
     CU(cudaFuncSetAttribute(fw::fw_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)fw::tile_smem_bytes(true)));
-    CU(cudaFuncSetAttribute(fw::fw_colpanel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(fw::fw_colpanel_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)fw::panel_smem_bytes()));
-    CU(cudaFuncSetAttribute(fw::fw_colpanel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(fw::fw_colpanel_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)fw::panel_smem_bytes()));
-    CU(cudaFuncSetAttribute(fw::fw_rowpanel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(fw::fw_colpanel_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)fw::panel_smem_bytes()));
-    CU(cudaFuncSetAttribute(fw::fw_rowpanel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU(cudaFuncSetAttribute(fw::fw_colpanel_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::panel_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_rowpanel_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::panel_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_rowpanel_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::panel_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_rowpanel_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)fw::panel_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_rowpanel_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)fw::panel_smem_bytes()));
     CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)fw::bulk_smem_bytes<2>()));
@@ -247,6 +255,24 @@ void launch_bulk(fw_ctx *c, fw::BulkArgs g, int ncu, int nru) {
 
 constexpr int NOSKIP = 0x3fffffff;
 
+// One phase-2 panel launch: `jobs` matrix rows (column panel) or columns (row panel), NJ per half-warp.
+template <bool COL>
+void launch_panel(fw_ctx *c, const fw::PanelArgs &p, int jobs, bool paths, cudaStream_t st) {
+    const int nj = fw::panel_nj(jobs, c->sm_count);
+    const int passes = jobs / (32 * nj);
+    const int grid = passes < c->sm_count ? passes : c->sm_count;
+    const size_t sm = fw::panel_smem_bytes();
+    if (COL) {
+        if (paths) { if (nj == 2) fw::fw_colpanel_kernel<true, 2><<<grid, 512, sm, st>>>(p); else fw::fw_colpanel_kernel<true, 1><<<grid, 512, sm, st>>>(p); }
+        else       { if (nj == 2) fw::fw_colpanel_kernel<false, 2><<<grid, 512, sm, st>>>(p); else fw::fw_colpanel_kernel<false, 1><<<grid, 512, sm, st>>>(p); }
+    } else {
+        if (paths) { if (nj == 2) fw::fw_rowpanel_kernel<true, 2><<<grid, 512, sm, st>>>(p); else fw::fw_rowpanel_kernel<true, 1><<<grid, 512, sm, st>>>(p); }
+        else       { if (nj == 2) fw::fw_rowpanel_kernel<false, 2><<<grid, 512, sm, st>>>(p); else fw::fw_rowpanel_kernel<false, 1><<<grid, 512, sm, st>>>(p); }
+    }
+    c->launches++;
+}
+
+
 // Domain check (synchronises the stream once).
 int validate_device(fw_ctx *c, const double *rate, const int32_t *next, long long ld, long long stride,
                     int batch, int n, int rows = -1, int row0 = 0) {
@@ -281,23 +307,18 @@ int launch_pivot_phases(fw_ctx *c, int npad, long long ld, double *rate, int32_t
     }
     c->launches++;
     if (panels) {
-        const int njobs32 = (npad - FW_B) / 32;
-        const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
         fw::PanelArgs p;
         p.rate = rate; p.next = next; p.mid = mid; p.csT = csT; p.rs = rs;
         p.ld = ld; p.npad = npad; p.b0 = b0; p.rows = npad; p.blk_r0 = b0; p.skip_r0 = b0; p.skipn = FW_B;
         p.Cp = c->Cp[set].p; p.ldc = npad; p.NCp = c->NCp[set].p; p.Rw = c->Rw[set].p; p.ldw = npad;
         {
             PhaseTimer pt(c, 1);
-            if (paths) fw::fw_colpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), (c->cur ? c->cur : c->stream)>>>(p);
-            else fw::fw_colpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), (c->cur ? c->cur : c->stream)>>>(p);
+            launch_panel<true>(c, p, npad - FW_B, paths, (c->cur ? c->cur : c->stream));
         }
         {
             PhaseTimer pt(c, 2);
-            if (paths) fw::fw_rowpanel_kernel<true><<<pgrid, 512, fw::panel_smem_bytes(), (c->cur ? c->cur : c->stream)>>>(p);
-            else fw::fw_rowpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), (c->cur ? c->cur : c->stream)>>>(p);
+            launch_panel<false>(c, p, npad - FW_B, paths, (c->cur ? c->cur : c->stream));
         }
-        c->launches += 2;
     }
     CU(cudaGetLastError());
     return FW_OK;
@@ -1091,11 +1112,8 @@ int fw_shard_pivot(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld,
         p.rate = d_rate; p.next = d_next; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
         p.ld = ld; p.npad = n; p.b0 = b0; p.rows = rows; p.blk_r0 = blk_r0; p.skip_r0 = blk_r0; p.skipn = FW_B;
         p.Cp = c->Cp[0].p; p.ldc = rows; p.NCp = c->NCp[0].p; p.Rw = d_Rw; p.ldw = n;
-        const int njobs32 = (n - FW_B) / 32;
-        const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
         PhaseTimer pt(c, 2);
-        fw::fw_rowpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
-        c->launches++;
+        launch_panel<false>(c, p, n - FW_B, false, c->stream);
     }
     CU(cudaGetLastError());
     return FW_OK;
@@ -1146,13 +1164,10 @@ int fw_shard_update_ex(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t
     p.rate = rate_v; p.next = next_v; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
     p.ld = ld; p.npad = n; p.b0 = b0; p.rows = vrows; p.blk_r0 = NOSKIP; p.skip_r0 = s0v; p.skipn = sn;
     p.Cp = cp_v; p.ldc = rows; p.NCp = ncp_v; p.Rw = const_cast<double *>(d_Rw); p.ldw = n;
-    const int njobs32 = rows_out / 32;
-    const int pgrid = njobs32 < c->sm_count ? njobs32 : c->sm_count;
     {
         PhaseTimer pt(c, 1);
-        fw::fw_colpanel_kernel<false><<<pgrid, 512, fw::panel_smem_bytes(), c->stream>>>(p);
+        launch_panel<true>(c, p, rows_out, false, c->stream);
     }
-    c->launches++;
     fw::BulkArgs g;
     g.rate = rate_v; g.next = next_v; g.mid = nullptr; g.ld = ld; g.b0 = b0; g.row0 = row0 + v0;
     g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
