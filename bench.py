@@ -156,6 +156,15 @@ def device_graph(n: int, seed: int, device):
     return rate, nxt
 
 
+def host_threads() -> int:
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    would make the CPU arm single-threaded under `--gpus N`; the oracle takes an explicit thread count."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def host_graph(n: int, seed: int):
     from floydwarshall_b200 import graphs
     return graphs.exchange_graph(n // CCY, CCY, seed)
@@ -177,7 +186,7 @@ def run_reference(args):
             n //= 2
     except Exception:  # noqa: BLE001
         pass
-    threads = O.max_threads()
+    threads = host_threads()
     rate, nxt = host_graph(n, SEED)
     ksteps = max(1, int(8 * (32768 / n) ** 2))          # ~8.6e9 relaxations per step
     ksteps = min(ksteps, max(1, n // (args.warmup + args.steps)))   # stay inside the n pivots
@@ -340,7 +349,7 @@ def run_ours(args):
             xh = torch.empty((n, n), dtype=torch.int32)
         rh.copy_(r0); xh.copy_(x0)
         torch.cuda.synchronize()
-        threads = O.max_threads()
+        threads = host_threads()
         ks = max(2, int(16 * (32768 / n) ** 2))
         O.run_ksteps(rh.numpy(), xh.numpy(), 0, 1, threads)      # warm the pages / threads
         t0 = time.perf_counter()
