@@ -187,33 +187,42 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
         load_chunk(ch0 + 1, 1);
     }
 #else
-    // cp.async sources/destinations of this thread, computed once: piece p = tid + 128*t covers
-    // A: row kk = (tid>>5) + 4t, 16 bytes at column (tid&31)*2;  B: likewise with TW/2 pieces per row.
-    // 32-bit element offsets of this thread's first piece inside a panel (panels are < 2^31 elements)
-    const int offA = (tid >> 5) * (int)a.ldc + i0 + (tid & 31) * 2;
-    const int offB = (tid / (TW / 2)) * (int)a.ldw + j0 + (tid % (TW / 2)) * 2;
-    const unsigned dstA = (unsigned)__cvta_generic_to_shared(&As[0][tid >> 5][(tid & 31) * 2]);
-    const unsigned dstB = (unsigned)__cvta_generic_to_shared(&Bs[0][tid / (TW / 2)][(tid % (TW / 2)) * 2]);
+    // cp.async staging.  A chunk is 16 panel rows of 512 B (A: CpT, 64 doubles) and 16 of TW*8 B (B: Rw).
+    // Thread tid owns row kk = tid >> 3 of both and, inside the row, the 16-byte pieces at byte offsets
+    // (tid & 7)*16 + t*128: all pieces of a thread hang off ONE pointer with constant offsets, and the eight
+    // lanes of a row cover 128 contiguous bytes per instruction.  The two pointers advance by 16 panel rows
+    // per chunk (two 64-bit adds) instead of being rebuilt from the kernel arguments (which cost ~60
+    // integer instructions per chunk, 4 % of the issue slots of a 16-step chunk).
     constexpr unsigned bufA = BULK_KC * BULK_TR * 8, bufB = BULK_KC * TW * 8;   // bytes per stage
+    const int prow = tid >> 3, pseg = (tid & 7) * 2;                              // row, first double of piece 0
+    const unsigned dstA = (unsigned)__cvta_generic_to_shared(&As[0][prow][pseg]);
+    const unsigned dstB = (unsigned)__cvta_generic_to_shared(&Bs[0][prow][pseg]);
+    const long long stepA = (long long)BULK_KC * a.ldc, stepB = (long long)BULK_KC * a.ldw;   // doubles per chunk
+    const int ch0 = kstart / BULK_KC, ch1 = a.nb * (FW_B / BULK_KC);
     // chunk c (0 .. nb*8-1) = steps [16c, 16c+16) relative to b0; chunks 8.. come from the second block's panels
-    auto load_chunk = [&](int c, int buf) {
-        const int set = c >> 3, kk0 = (c & 7) * BULK_KC;
-        const double *pa = a.CpT[set] + ((long long)kk0 * a.ldc + offA);
-        const double *pb = a.Rw[set] + ((long long)kk0 * a.ldw + offB);
+    const double *pa = a.CpT[ch0 >> 3] + ((long long)((ch0 & 7) * BULK_KC + prow) * a.ldc + i0 + pseg);
+    const double *pb = a.Rw[ch0 >> 3] + ((long long)((ch0 & 7) * BULK_KC + prow) * a.ldw + j0 + pseg);
+    int cnext = ch0;                          // the chunk pa / pb point at
+    auto load_chunk = [&](int buf) {          // loads chunk `cnext` into stage `buf`, then advances
 #pragma unroll
         for (int t = 0; t < 4; ++t)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dstA + buf * bufA + t * (4 * BULK_TR * 8)),
-                         "l"(pa + (long long)t * 4 * a.ldc));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dstA + buf * bufA + t * 128), "l"(pa + t * 16));
 #pragma unroll
-        for (int t = 0; t < 2 * CQ; ++t)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dstB + buf * bufB + t * ((128 / (TW / 2)) * TW * 8)),
-                         "l"(pb + (long long)t * (128 / (TW / 2)) * a.ldw));
+        for (int t = 0; t < TW / 16; ++t)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dstB + buf * bufB + t * 128), "l"(pb + t * 16));
+        ++cnext;
+        if (cnext == FW_B / BULK_KC) {        // first chunk of the second k-block: switch panel sets
+            pa = a.CpT[1] + ((long long)prow * a.ldc + i0 + pseg);
+            pb = a.Rw[1] + ((long long)prow * a.ldw + j0 + pseg);
+        } else {
+            pa += stepA;
+            pb += stepB;
+        }
     };
 
-    const int ch0 = kstart / BULK_KC, ch1 = a.nb * (FW_B / BULK_KC);
-    load_chunk(ch0, 0);
+    load_chunk(0);
     cp_async_commit();
-    load_chunk(ch0 + 1, 1);
+    load_chunk(1);
     cp_async_commit();
 
 #endif
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
         if (ch + 1 < ch1) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();   // (a) chunk ch visible to all; (b) everyone is done with chunk ch-1's buffer
         if (ch + 2 < ch1) {
-            load_chunk(ch + 2, buf == 0 ? 2 : buf - 1);   // (buf + 2) % 3 == the buffer chunk ch-1 used
+            load_chunk(buf == 0 ? 2 : buf - 1);   // chunk ch+2 into (buf + 2) % 3 == the buffer chunk ch-1 used
             cp_async_commit();
         }
 #endif
