@@ -151,6 +151,7 @@ struct fw_ctx {
     DevBuf<int32_t> NCp[4];
     bool fuse_pairs = true;        // knob FW_FUSE_PAIRS=0 turns pairing off, =2 forces it for every size
     bool fuse_forced = false;
+    int panel_nj = 0;              // knob FW_PANEL_NJ=1|2 forces the jobs per half-warp of the panel kernels (0: by size)
     // padded working copy (n not a multiple of FW_B) and host-API staging
     DevBuf<double> w_rate;
     DevBuf<int32_t> w_next, w_mid, w_csT, w_rs;
@@ -201,6 +202,7 @@ int set_kernel_attrs(fw_ctx *c) {
     CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     if (const char *e = getenv("FW_BULK_CQ")) c->bulk_cq = atoi(e) == 4 ? 4 : 2;
     if (const char *e = getenv("FW_FUSE_PAIRS")) { c->fuse_pairs = atoi(e) != 0; c->fuse_forced = atoi(e) == 2; }
+    if (const char *e = getenv("FW_PANEL_NJ")) c->panel_nj = atoi(e);
     if (const char *e = getenv("FW_BULK_BAND")) c->bulk_band = atoi(e) > 0 ? atoi(e) : 64;
     c->attrs_set = true;
     return FW_OK;
@@ -258,7 +260,7 @@ constexpr int NOSKIP = 0x3fffffff;
 // One phase-2 panel launch: `jobs` matrix rows (column panel) or columns (row panel), NJ per half-warp.
 template <bool COL>
 void launch_panel(fw_ctx *c, const fw::PanelArgs &p, int jobs, bool paths, cudaStream_t st) {
-    const int nj = fw::panel_nj(jobs, c->sm_count);
+    const int nj = (c->panel_nj == 1 || c->panel_nj == 2) ? c->panel_nj : fw::panel_nj(jobs, c->sm_count);
     const int passes = jobs / (32 * nj);
     const int grid = passes < c->sm_count ? passes : c->sm_count;
     const size_t sm = fw::panel_smem_bytes();
