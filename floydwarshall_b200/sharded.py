@@ -87,6 +87,55 @@ def run_schedule_lookahead(backend, n: int, rank: int, world: int, rt) -> None:
         rt.a_done()
 
 
+def run_schedule_lookahead_pairs(backend, n: int, rank: int, world: int, rt) -> None:
+    """run_schedule_lookahead with the k-blocks taken in PAIRS (p = blocks 2p, 2p+1), so that the bulk
+    kernel loads every tile of the shard once per 256 steps (backend.update_pair).  A pair never straddles
+    two ranks (rows per rank is a multiple of 2B).  Per pair its owner factors both blocks on the look-ahead
+    lane -- pivot(2p), broadcast, the 128 rows of block 2p+1 take block 2p, pivot(2p+1), broadcast -- after
+    bringing the pair's 256 rows up to date with the previous pair; the main lane gives every other local
+    row both blocks in one update_pair, and the owner's rows of block 2p take block 2p+1 on their own.
+    Panel buffers: pair p uses backend.Rw buffers 2*(p&1) and 2*(p&1)+1."""
+    rows = shard_rows(n, world)
+    if rows % (2 * B) != 0:
+        raise ValueError(f"pairs need rows per rank ({rows}) to be a multiple of {2 * B}")
+    npair = n // (2 * B)
+
+    def factor(p):
+        b0, s = 2 * p * B, 2 * (p & 1)
+        owner = b0 // rows
+        if rank == owner:
+            backend.pivot(b0, s)
+        if world > 1:
+            rt.bcast(s, owner)
+        if rank == owner:
+            backend.update(b0, s, 1, (b0 + B) - rank * rows)     # rows of the second block take the first
+            backend.pivot(b0 + B, s + 1)
+        if world > 1:
+            rt.bcast(s + 1, owner)
+
+    with rt.lane_b():
+        factor(0)
+    rt.b_done()
+    for p in range(npair):
+        b0, s = 2 * p * B, 2 * (p & 1)
+        nxt = p + 1 < npair
+        own = (b0 // rows == rank)
+        own_next = nxt and ((b0 + 2 * B) // rows == rank)
+        lr_next = (b0 + 2 * B) - rank * rows
+        rt.wait_b_done()                      # both panels of pair p are here
+        if nxt:
+            with rt.lane_b():
+                rt.wait_a_done()              # pair p-1 is finished: the rows of pair p+1 and its buffers are free
+                if own_next:
+                    backend.update_pair(b0, s, 1, lr_next, 2 * B)   # only the next pair's 256 rows
+                factor(p + 1)
+                rt.b_done()
+        backend.update_pair(b0, s, 2 if own_next else 0, lr_next if own_next else 0, 2 * B if own_next else 0)
+        if own:
+            backend.update(b0 + B, s + 1, 1, b0 - rank * rows)       # the first block's rows take the second
+        rt.a_done()
+
+
 class SerialRuntime:
     """Both lanes are the caller's thread (CPU tests): events are no-ops."""
 
@@ -176,7 +225,7 @@ class GpuShardBackend:
         assert rate_t.shape[1] == n and rate_t.dtype == torch.float64 and next_t.dtype == torch.int32
         self.ctx, self.n, self.row0, self.rows = ctx, n, row0, rate_t.shape[0]
         self.rate, self.next = rate_t, next_t
-        self.Rw2 = [torch.empty((B, n), dtype=torch.float64, device=rate_t.device) for _ in range(2)]
+        self.Rw2 = [torch.empty((B, n), dtype=torch.float64, device=rate_t.device) for _ in range(4)]
         self.Rw = self.Rw2[0]
         self.L = _lib.load()
         self.launches = 0
@@ -199,13 +248,25 @@ class GpuShardBackend:
                                              mode, lr0))
         self.launches += self.ctx.last_launches
 
+    def update_pair(self, b0: int, buf: int = 0, mode: int = 0, lr0: int = 0, lrn: int = 0):
+        _lib.check(self.L.fw_shard_update_pair(self.ctx.handle, self.n, self.row0, self.rows, self.n,
+                                               self._p(self.rate), self._p(self.next), b0, self._p(self.Rw2[buf]),
+                                               self._p(self.Rw2[buf + 1]), mode, lr0, lrn))
+        self.launches += self.ctx.last_launches
+
+
+PAIRS = os.environ.get("FW_SHARD_PAIRS", "1") != "0"     # k-blocks in pairs when the shard geometry allows it
+
 
 def solve_shard(backend, n: int, rank: int, world: int, lookahead: bool = True):
     """Run the k-block schedule on a GpuShardBackend (collective: call on every rank)."""
     import torch.distributed as dist
     if lookahead:
         rt = TorchRuntime(backend, world)
-        run_schedule_lookahead(backend, n, rank, world, rt)
+        if PAIRS and shard_rows(n, world) % (2 * B) == 0:
+            run_schedule_lookahead_pairs(backend, n, rank, world, rt)
+        else:
+            run_schedule_lookahead(backend, n, rank, world, rt)
         rt.finish()
     else:
         run_schedule(backend, n, rank, world, lambda owner: dist.broadcast(backend.Rw, src=owner))

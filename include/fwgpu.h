@@ -188,6 +188,18 @@ int fw_shard_update(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t 
 int fw_shard_update_ex(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
                        double *d_rate, int32_t *d_next, int32_t b0, const double *d_Rw,
                        int32_t mode, int32_t lr0);
+/* Two CONSECUTIVE k-blocks b0, b0+128 in one call, so that the bulk kernel loads every tile of the
+ * shard once per 256 steps (the single-GPU solve's pairing): column panel of b0, bulk(b0) on the
+ * column strip of b0+128, column panel of b0+128, then one fused bulk launch.  d_Rw0 / d_Rw1 are the
+ * row-snapshot panels of the two blocks (both pivoted and broadcast before the call).  Needs row0,
+ * rows, b0 multiples of 256.  Rows: mode 0 = every local row outside the pair's own 256 rows;
+ * mode 1 = ONLY the lrn local rows starting at lr0; mode 2 = mode 0 minus those rows (adjacent to
+ * the pair's rows when the shard owns them).  The pair's own rows are the owner's business:
+ * fw_shard_pivot(b0), fw_shard_update_ex(b0, mode 1, rows of b0+128), fw_shard_pivot(b0+128) before
+ * the broadcasts, fw_shard_update_ex(b0+128, mode 1, rows of b0) after them. */
+int fw_shard_update_pair(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
+                         double *d_rate, int32_t *d_next, int32_t b0, const double *d_Rw0,
+                         const double *d_Rw1, int32_t mode, int32_t lr0, int32_t lrn);
 
 /* Block until everything queued on the context's stream has finished and
  * report any asynchronous failure (incl. FW_ERR_DOMAIN of *_device calls). */

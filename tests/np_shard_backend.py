@@ -10,7 +10,7 @@ class NumpyShardBackend:
     def __init__(self, n, row0, rate, nxt, block=B):
         self.n, self.row0, self.rows, self.B = n, row0, rate.shape[0], block
         self.rate, self.next = rate, nxt
-        self.Rw2 = [np.zeros((block, n)), np.zeros((block, n))]
+        self.Rw2 = [np.zeros((block, n)) for _ in range(4)]
         self.Rw = self.Rw2[0]
         self.Cp = np.zeros((self.rows, block))
         self.NCp = np.zeros((self.rows, block), dtype=np.int32)
@@ -56,20 +56,24 @@ class NumpyShardBackend:
         self.next[lr:lr + B_, out] = XX
         Rw[:, out] = Rwo
 
-    def update(self, b0, buf=0, mode=0, lr0=0):
-        """mode 0: all rows outside the k-block; 1: only rows [lr0, lr0+B); 2: mode 0 minus those rows."""
+    def update(self, b0, buf=0, mode=0, lr0=0, lrn=None, extra_skip=None):
+        """mode 0: all rows outside the k-block; 1: only rows [lr0, lr0+lrn); 2: mode 0 minus those rows.
+        extra_skip: (first local row, count) additionally left out (the other block of a pair)."""
         B_ = self.B
+        lrn = B_ if lrn is None else lrn
         Rw = self.Rw2[buf]
         ks = slice(b0, b0 + B_)
         rout = np.ones(self.rows, bool)
         if self.row0 <= b0 < self.row0 + self.rows:
             rout[b0 - self.row0:b0 - self.row0 + B_] = False
+        if extra_skip is not None and 0 <= extra_skip[0] < self.rows:
+            rout[extra_skip[0]:extra_skip[0] + extra_skip[1]] = False
         if mode == 1:
             only = np.zeros(self.rows, bool)
-            only[lr0:lr0 + B_] = True
+            only[lr0:lr0 + lrn] = True
             rout &= only
         elif mode == 2:
-            rout[lr0:lr0 + B_] = False
+            rout[lr0:lr0 + lrn] = False
         if not rout.any():
             return
         Y = self.rate[rout][:, ks]
@@ -95,3 +99,10 @@ class NumpyShardBackend:
             self._relax(Rb, Xb, self.Cp[ridx, kk], self.NCp[ridx, kk], Rw[kk, cidx])
         self.rate[np.ix_(ridx, cidx)] = Rb
         self.next[np.ix_(ridx, cidx)] = Xb
+
+    def update_pair(self, b0, buf=0, mode=0, lr0=0, lrn=0):
+        """k-blocks b0 and b0+B (panels Rw2[buf], Rw2[buf+1]) on every local row outside the PAIR's own
+        rows (modes as in update): by definition the two single-block updates one after the other."""
+        B_ = self.B
+        self.update(b0, buf, mode, lr0, lrn, extra_skip=(b0 + B_ - self.row0, B_))
+        self.update(b0 + B_, buf + 1, mode, lr0, lrn, extra_skip=(b0 - self.row0, B_))

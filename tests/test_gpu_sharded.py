@@ -70,6 +70,67 @@ def test_virtual_ranks_on_one_gpu(world, E, C, mode, lookahead):
         c.close()
 
 
+@pytest.mark.parametrize("world,E,C,mode", [(1, 32, 16, "consistent"), (2, 32, 16, "arbitrage"),
+                                            (2, 64, 16, "consistent"), (4, 64, 16, "pow2")])
+def test_virtual_ranks_pairs_on_one_gpu(world, E, C, mode):
+    """The call sequence of sharded.run_schedule_lookahead_pairs (fw_shard_update_pair: two k-blocks per
+    bulk launch), serialised on one stream; n = 512 / 1024 so that a rank owns one or two whole pairs."""
+    import torch
+    n = E * C
+    B = sharded.B
+    rate, nxt = graphs.exchange_graph(E, C, seed=33, density=0.7, mode=mode)
+    ref = O.solve_dense(rate, nxt, threads=0)
+    rows = sharded.shard_rows(n, world)
+    assert rows % (2 * B) == 0
+    ctxs = [_lib.Context(0) for _ in range(world)]
+    stream = torch.cuda.current_stream().cuda_stream
+    bes = []
+    for r in range(world):
+        ctxs[r].set_stream(stream)
+        rt = torch.from_numpy(rate[r * rows:(r + 1) * rows].copy()).cuda()
+        xt = torch.from_numpy(nxt[r * rows:(r + 1) * rows].copy()).cuda()
+        be = sharded.GpuShardBackend(ctxs[r], n, r * rows, rt, xt)
+        be.validate()
+        bes.append(be)
+
+    def share(buf, owner):                      # stands in for dist.broadcast(Rw[buf], src=owner)
+        for r in range(world):
+            if r != owner:
+                bes[r].Rw2[buf].copy_(bes[owner].Rw2[buf])
+
+    def factor(p):
+        b0, s = 2 * p * B, 2 * (p & 1)
+        ow = b0 // rows
+        bes[ow].pivot(b0, s)
+        share(s, ow)
+        bes[ow].update(b0, s, 1, (b0 + B) - ow * rows)
+        bes[ow].pivot(b0 + B, s + 1)
+        share(s + 1, ow)
+
+    npair = n // (2 * B)
+    factor(0)
+    for p in range(npair):
+        b0, s = 2 * p * B, 2 * (p & 1)
+        on = (b0 + 2 * B) // rows if p + 1 < npair else -1
+        if on >= 0:
+            bes[on].update_pair(b0, s, 1, (b0 + 2 * B) - on * rows, 2 * B)
+            factor(p + 1)
+        for r in range(world):
+            if r == on:
+                bes[r].update_pair(b0, s, 2, (b0 + 2 * B) - r * rows, 2 * B)
+            else:
+                bes[r].update_pair(b0, s, 0, 0, 0)
+        ow = b0 // rows
+        bes[ow].update(b0 + B, s + 1, 1, b0 - ow * rows)
+    torch.cuda.synchronize()
+    got_r = np.concatenate([be.rate.cpu().numpy() for be in bes])
+    got_x = np.concatenate([be.next.cpu().numpy() for be in bes])
+    assert np.array_equal(got_r.view(np.uint64), ref.rate.view(np.uint64))
+    assert np.array_equal(got_x, ref.next)
+    for c in ctxs:
+        c.close()
+
+
 def test_device_graph_shard_matches_host_generator():
     import torch
     n, ccy = 512, 16

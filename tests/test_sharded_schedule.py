@@ -37,7 +37,9 @@ def _worker(rank, world, port, n, block, mode, out_dir, lookahead=False):
 
     sharded.B = block      # the schedule is block-size agnostic; shrink it so the test is fast
     try:
-        if lookahead:
+        if lookahead == "pairs":
+            sharded.run_schedule_lookahead_pairs(be, n, rank, world, sharded.SerialRuntime(bcast2))
+        elif lookahead:
             sharded.run_schedule_lookahead(be, n, rank, world, sharded.SerialRuntime(bcast2))
         else:
             sharded.run_schedule(be, n, rank, world, bcast)
@@ -50,13 +52,13 @@ def _worker(rank, world, port, n, block, mode, out_dir, lookahead=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("lookahead", [False, True])
+@pytest.mark.parametrize("lookahead", [False, True, "pairs"])
 @pytest.mark.parametrize("mode", ["consistent", "arbitrage"])
 def test_two_rank_schedule_matches_oracle(tmp_path, mode, lookahead):
     from floydwarshall_b200 import graphs
     from oracle import fw_oracle as O
     n, block, world = 64, 8, 2
-    port = 29500 + (os.getpid() % 2000) + (7 if lookahead else 0)
+    port = 29500 + (os.getpid() % 2000) + {False: 0, True: 7, "pairs": 13}[lookahead]
     mp.spawn(_worker, args=(world, port, n, block, mode, str(tmp_path), lookahead), nprocs=world, join=True)
     rate, nxt = graphs.exchange_graph(n // 8, 8, seed=21, density=0.8, mode=mode)
     ref = O.solve_dense(rate, nxt)
