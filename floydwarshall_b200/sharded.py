@@ -9,6 +9,9 @@ One process per GPU (torch.distributed, NCCL).  Rank r keeps rows
 
 Only Rw travels: next-hops are row-local (NX[i][j] <- NX[i][k]), and the column
 snapshots every rank needs for its own rows come out of its own column panel.
+By default the k-blocks are taken in PAIRS with a look-ahead lane
+(run_schedule_lookahead_pairs / fw_shard_update_pair): two broadcasts per pair,
+one fused bulk launch per pair and rank.
 The schedule is backend-agnostic: the GPU backend drives libfwgpu's fw_shard_*
 entry points; tests drive the same schedule with a numpy backend under gloo.
 """
@@ -452,7 +455,7 @@ def bench_main(args, METRIC, UNIT, SEED, workload_n, workload_name, ClockSampler
             "config": {"workload": workload_name(n), "n": n, "seed": SEED + 1, "k_block": B,
                        "sharding": f"row blocks of {rows} rows per rank; per-k-block NCCL broadcast of the "
                                    f"128 x {n} fp64 pivot-row snapshot panel ({B * n * 8 / 2**20:.0f} MiB)",
-                       "lookahead": LOOKAHEAD,
+                       "lookahead": LOOKAHEAD, "k_blocks_in_pairs": bool(LOOKAHEAD and PAIRS and rows % (2 * B) == 0),
                        "l2": "per-rank inputs are far larger than the 126 MB L2; no flush needed",
                        "check": check},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()),
