@@ -36,20 +36,22 @@ struct BulkArgs {
     long long ld;
     int b0;                // first pivot of the (first) k-block (global)
     int row0;              // global index of local row 0 (row shards; 0 otherwise)
-    // One launch applies nb (1 or 2) CONSECUTIVE k-blocks [b0, b0 + nb*128) to every selected tile,
+    // One launch applies nb (1 .. BULK_MAXNB) CONSECUTIVE k-blocks [b0, b0 + nb*128) to every selected tile,
     // from per-block snapshot panels:
     int nb;
-    const double *CpT[2];  // B x rows  column snapshots, transposed: CpT[kk*ldc + i]
-    const int32_t *NCp[2]; // rows x B  next-hop snapshots: NCp[i*B + kk]
-    const double *Rw[2];   // B x N     row snapshots: Rw[kk*ldw + j]
+    const double *CpT[8];  // B x rows  column snapshots, transposed: CpT[kk*ldc + i]
+    const int32_t *NCp[8]; // rows x B  next-hop snapshots: NCp[i*B + kk]
+    const double *Rw[8];   // B x N     row snapshots: Rw[kk*ldw + j]
     long long ldc, ldw;
     // Tile selection, in tile units (64 local rows / TW columns): grid (x, y) -> tile
     //   tj = col_lo + x, += cskipn if tj >= cskip0;   ti = row_lo + y, += rskipn if ti >= rskip0
     int row_lo, rskip0, rskipn;
     int col_lo, cskip0, cskipn;   // in units of 64 columns (scaled by 64/TW inside the kernel)
-    // nb == 2: tiles in the strips of the FIRST block (tile rows [half_r0, half_r0+2) or tile columns
-    // of the first block) already took its 128 steps in phase 2 and only run the second block's.
-    int half_r0, half_c0;         // tile row / 64-column unit of the first block; huge if none
+    // nb > 1: a tile in the row or column strip of the group's block i (i < nb-1; strips of consecutive
+    // blocks are adjacent, 2 tile rows / 128 columns each) already took blocks 0..i (phase 2 of block i and
+    // the strip launches before it) and starts at block i+1.  half_r0 / half_c0 = first tile row / first
+    // 64-column unit of the group's FIRST block; huge if none.
+    int half_r0, half_c0;
     // 1-D grid of gx*gy CTAs, rasterised in column bands of `band` tile columns: a band's slice of the
     // row-snapshot panels (band*TW columns x 256 steps x 8 B, a few MB) stays hot in L2 while the CTAs
     // sweep all tile rows, instead of the whole 64 MB panel being re-streamed for every tile row.
@@ -57,6 +59,7 @@ struct BulkArgs {
 };
 
 constexpr int BULK_TR = 64;   // tile rows
+constexpr int BULK_MAXNB = 8; // most k-blocks per fused launch
 constexpr int BULK_KC = 16;   // k-chunk
 constexpr int BULK_ST = 3;    // cp.async pipeline stages (one __syncthreads per chunk)
 #ifndef FW_BULK_UNROLL
@@ -148,9 +151,12 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
     if (tj >= a.cskip0 / CU) tj += a.cskipn / CU;
     const int i0 = ti * BULK_TR, j0 = tj * TW;
     int kstart = 0;
-    if (a.nb == 2 && ((ti >= a.half_r0 && ti < a.half_r0 + FW_B / BULK_TR) ||
-                      (tj >= a.half_c0 / CU && tj < a.half_c0 / CU + FW_B / TW)))
-        kstart = FW_B;
+    if (a.nb > 1) {
+        const int dr = ti - a.half_r0, dc = tj - a.half_c0 / CU;     // distance from the first block's strips
+        const int br = (dr >= 0 && dr < (a.nb - 1) * (FW_B / BULK_TR)) ? dr / (FW_B / BULK_TR) + 1 : 0;
+        const int bc = (dc >= 0 && dc < (a.nb - 1) * (FW_B / TW)) ? dc / (FW_B / TW) + 1 : 0;
+        kstart = max(br, bc) * FW_B;
+    }
     const long long ld = a.ld;
 
 #if FW_BULK_TMA
@@ -174,7 +180,7 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
     const long long poff = isA ? ((long long)prow * a.ldc + i0) : ((long long)prow * a.ldw + j0);
     const unsigned pdst = isA ? (unsigned)__cvta_generic_to_shared(&As[0][prow][0]) : (unsigned)__cvta_generic_to_shared(&Bs[0][prow][0]);
     auto load_chunk = [&](int c, int stage) {       // warp 0 only
-        const int set = c >> 3, kk0 = (c & 7) * BULK_KC;
+        const int set = c >> 3, kk0 = (c & 7) * BULK_KC;   // TMA variant
         const unsigned full = bar0 + 8 * stage;
         if (lane == 0) mbar_expect_tx(full, bufA + bufB);
         __syncwarp();
@@ -211,9 +217,10 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
         for (int t = 0; t < TW / 16; ++t)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dstB + buf * bufB + t * 128), "l"(pb + t * 16));
         ++cnext;
-        if (cnext == FW_B / BULK_KC) {        // first chunk of the second k-block: switch panel sets
-            pa = a.CpT[1] + ((long long)prow * a.ldc + i0 + pseg);
-            pb = a.Rw[1] + ((long long)prow * a.ldw + j0 + pseg);
+        if ((cnext & (FW_B / BULK_KC - 1)) == 0) {        // first chunk of the next k-block: switch panel sets
+            const int set = min(cnext / (FW_B / BULK_KC), BULK_MAXNB - 1);   // (one past the last: never loaded)
+            pa = a.CpT[set] + ((long long)prow * a.ldc + i0 + pseg);
+            pb = a.Rw[set] + ((long long)prow * a.ldw + j0 + pseg);
         } else {
             pa += stepA;
             pb += stepB;

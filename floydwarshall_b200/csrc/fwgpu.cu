@@ -147,10 +147,10 @@ struct fw_ctx {
     std::mutex mu;
     int64_t launches = 0;
     // snapshot panels
-    DevBuf<double> Cp[4], Rw[4];   // panel sets: k-blocks go in pairs, and the next pair is factored ahead
-    DevBuf<int32_t> NCp[4];
-    bool fuse_pairs = true;        // knob FW_FUSE_PAIRS=0 turns pairing off, =2 forces it for every size
-    bool fuse_forced = false;
+    DevBuf<double> Cp[16], Rw[16];   // panel sets: k-blocks go in groups of up to 8, and the next group is factored ahead
+    DevBuf<int32_t> NCp[16];
+    int fuse_group = 0;            // k-blocks per fused bulk launch, 0 = by size: knob FW_FUSE_GROUP=1|2|4|8 (forces it for every
+    bool fuse_forced = false;      // size); FW_FUSE_PAIRS=0 / =2 kept as aliases of FW_FUSE_GROUP=1 / =2
     int panel_nj = 0;              // knob FW_PANEL_NJ=1|2 forces the jobs per half-warp of the panel kernels (0: by size)
     // padded working copy (n not a multiple of FW_B) and host-API staging
     DevBuf<double> w_rate;
@@ -201,7 +201,11 @@ int set_kernel_attrs(fw_ctx *c) {
                             (int)fw::bulk_smem_bytes<4>()));
     CU(cudaFuncSetAttribute(fw::fw_bulk_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     if (const char *e = getenv("FW_BULK_CQ")) c->bulk_cq = atoi(e) == 4 ? 4 : 2;
-    if (const char *e = getenv("FW_FUSE_PAIRS")) { c->fuse_pairs = atoi(e) != 0; c->fuse_forced = atoi(e) == 2; }
+    if (const char *e = getenv("FW_FUSE_PAIRS")) { c->fuse_group = atoi(e) != 0 ? 2 : 1; c->fuse_forced = atoi(e) == 2; }
+    if (const char *e = getenv("FW_FUSE_GROUP")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) { c->fuse_group = v; c->fuse_forced = true; }
+    }
     if (const char *e = getenv("FW_PANEL_NJ")) c->panel_nj = atoi(e);
     if (const char *e = getenv("FW_BULK_BAND")) c->bulk_band = atoi(e) > 0 ? atoi(e) : 64;
     c->attrs_set = true;
@@ -328,55 +332,67 @@ int launch_pivot_phases(fw_ctx *c, int npad, long long ld, double *rate, int32_t
 
 // Blocked solve on a padded (npad % FW_B == 0, pads = NaN) device matrix.
 //
-// k-blocks are taken in GROUPS of two (b, b+1) so that the bulk kernel loads every tile once per
-// 256 steps, and the pivot phases of the NEXT group run on a high-priority side stream while the
-// bulk of the current group is still busy:
+// k-blocks are taken in GROUPS of G = 1, 2 or 4 consecutive blocks so that the bulk kernel loads every
+// tile once per G*128 steps, and the pivot phases of the NEXT group run on a high-priority side stream
+// while the bulk of the current group is still busy:
 //
 //   main stream : bulk(G) on the strips of G'  | record E1 |  bulk(G) on everything else
-//   side stream :                    wait E1 -> phases 1+2 of b', bulk(b') on the strips of b'+1,
-//                                               phases 1+2 of b'+1 | record E2          (G' = {b', b'+1})
+//   side stream :                    wait E1 -> for every block b'+j of G' in turn: the earlier blocks of G'
+//                                               on the strips of b'+j (one fused launch of j blocks per
+//                                               strip direction), then phases 1+2 of b'+j | record E2
 //   next group  : main waits E2
 //
-// bulk(G) gives tiles outside both strips of G 256 steps and tiles in the first block's strips the
-// second 128 (phase 2 of the first block already gave them the first).  The order of relaxations
-// seen by every entry is unchanged (ascending k), so results are identical to the plain loop.
+// bulk(G) gives tiles outside all strips of G all G*128 steps, and a tile in the strips of the group's
+// block i only the blocks after i (phase 2 of block i and the strip launches gave it blocks 0..i); the
+// strips of the group's last block are complete and left out.  The order of relaxations seen by every
+// entry is unchanged (ascending k), so results are identical to the plain loop.
 int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next, int32_t *mid,
                   int32_t *csT, int32_t *rs) {
+    constexpr int GMAX = fw::BULK_MAXNB;
     int rc;
-    for (int set = 0; set < 4; ++set) {
+    const int nblk = npad / FW_B;
+    const int nu = npad / 64;                 // 64-row / 64-column units
+    // grouping splits every bulk launch in three and adds strip launches; below ~48 k-blocks the extra
+    // launches cost more than the saved tile loads (N=1024: 2.26 ms ungrouped vs 2.50 ms in pairs)
+    // Measured (ms per solve, groups of 1 / 2 / 4 / 8): N=8192 90.5 / 87.2 / 84.6 / 86.5, N=16384 - / 607 / 589 / 581,
+    // N=32768 - / 4560 / 4441 / -.  Larger groups move more work into the small strip launches.
+    const int gsz = c->fuse_forced ? c->fuse_group
+                                   : (c->fuse_group == 1 ? 1 : (nblk >= 128 ? 8 : (nblk >= 48 ? 4 : 1)));
+    for (int set = 0; set < (gsz == 1 ? 2 : 2 * gsz); ++set) {
         if ((rc = c->Cp[set].ensure((size_t)npad * FW_B)) != FW_OK) return rc;
         if ((rc = c->NCp[set].ensure((size_t)npad * FW_B)) != FW_OK) return rc;
         if ((rc = c->Rw[set].ensure((size_t)npad * FW_B)) != FW_OK) return rc;
     }
-    const int nblk = npad / FW_B;
-    const int nu = npad / 64;                 // 64-row / 64-column units
-    // pairing splits every bulk launch in three; below ~48 k-blocks the extra launches cost more than the
-    // second tile load saves (N=1024: 2.26 ms unpaired vs 2.50 ms paired; N=8192: 90.5 vs 87.4 ms)
-    const int gsz = (c->fuse_pairs && (nblk >= 48 || c->fuse_forced)) ? 2 : 1;
     cudaStream_t S = c->stream;
     cudaStream_t T = (c->overlap && c->side_stream) ? c->side_stream : c->stream;
     const bool two = (T != S);
     fw::BulkArgs g;
     g.rate = rate; g.next = next; g.mid = mid; g.ld = ld; g.row0 = 0; g.ldc = npad; g.ldw = npad;
     auto use_sets = [&](int s0) {
-        for (int i = 0; i < 2; ++i) {
-            g.CpT[i] = c->Cp[s0 + i].p; g.NCp[i] = c->NCp[s0 + i].p; g.Rw[i] = c->Rw[s0 + i].p;
+        for (int i = 0; i < GMAX; ++i) {
+            const int s = s0 + (i < gsz ? i : 0);
+            g.CpT[i] = c->Cp[s].p; g.NCp[i] = c->NCp[s].p; g.Rw[i] = c->Rw[s].p;
         }
     };
-    // phases 1+2 of the group starting at block b (gn blocks) into panel sets s0, s0+1 -- on c->cur
+    // phases 1+2 of the group starting at block b (gn blocks) into panel sets s0 .. s0+gn-1 -- on c->cur
     auto pivot_group = [&](int b, int gn, int s0) -> int {
         const int b0 = b * FW_B, u0 = b0 / 64;
         int r = launch_pivot_phases(c, npad, ld, rate, next, mid, csT, rs, b0, s0, nblk > 1);
-        if (r != FW_OK || gn == 1) return r;
-        use_sets(s0);
-        g.b0 = b0; g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
-        g.row_lo = u0 + 2; g.rskip0 = NOSKIP; g.rskipn = 0;          // the 2 tile rows of b+1 ...
-        g.col_lo = 0; g.cskip0 = u0; g.cskipn = 2;                   // ... x all columns outside b
-        launch_bulk(c, g, nu - 2, 2);
-        g.row_lo = 0; g.rskip0 = u0; g.rskipn = 4;                   // all rows outside b and b+1 ...
-        g.col_lo = u0 + 2; g.cskip0 = NOSKIP; g.cskipn = 0;          // ... x the 2 tile columns of b+1
-        launch_bulk(c, g, 2, nu - 4);
-        return launch_pivot_phases(c, npad, ld, rate, next, mid, csT, rs, b0 + FW_B, s0 + 1, true);
+        for (int j = 1; j < gn && r == FW_OK; ++j) {
+            // blocks b .. b+j-1 on the strips of block b+j (its pivot rows / columns must be current);
+            // the strips of b+j-1 are complete, tiles in the strips of an earlier block start after it
+            const int uj = u0 + 2 * j;
+            use_sets(s0);
+            g.b0 = b0; g.nb = j; g.half_r0 = u0; g.half_c0 = u0;
+            g.row_lo = uj; g.rskip0 = NOSKIP; g.rskipn = 0;          // the 2 tile rows of b+j ...
+            g.col_lo = 0; g.cskip0 = uj - 2; g.cskipn = 2;           // ... x all columns outside b+j-1
+            launch_bulk(c, g, nu - 2, 2);
+            g.row_lo = 0; g.rskip0 = uj - 2; g.rskipn = 4;           // all rows outside b+j-1 and b+j ...
+            g.col_lo = uj; g.cskip0 = NOSKIP; g.cskipn = 0;          // ... x the 2 tile columns of b+j
+            launch_bulk(c, g, 2, nu - 4);
+            r = launch_pivot_phases(c, npad, ld, rate, next, mid, csT, rs, b0 + j * FW_B, s0 + j, true);
+        }
+        return r;
     };
 
     if (two) { CU(cudaEventRecord(c->ev_main, S)); CU(cudaStreamWaitEvent(T, c->ev_main, 0)); }
@@ -394,7 +410,7 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
         if (two) CU(cudaStreamWaitEvent(S, c->ev_side, 0));             // panels of this group are ready
         use_sets(sbase);
         g.b0 = b0; g.nb = gn;
-        g.half_r0 = (gn == 2) ? u0 : NOSKIP; g.half_c0 = (gn == 2) ? u0 : NOSKIP;
+        g.half_r0 = (gn > 1) ? u0 : NOSKIP; g.half_c0 = (gn > 1) ? u0 : NOSKIP;
         if (gnn > 0) {
             const int uN = uL + 2;                                      // units of the next group: [uN, uN + 2*gnn)
             // (1) the next group's pivot rows / columns first
@@ -411,7 +427,7 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
             launch_bulk(c, g, nu - 2 - 2 * gnn, nu - 2 - 2 * gnn);
             // ... while the side stream factors the next group
             c->cur = T;
-            if ((rc = pivot_group(bn, gnn, sbase ^ 2)) != FW_OK) { c->cur = nullptr; return rc; }
+            if ((rc = pivot_group(bn, gnn, sbase ^ gsz)) != FW_OK) { c->cur = nullptr; return rc; }
             if (two) CU(cudaEventRecord(c->ev_side, T));
         } else {
             g.row_lo = 0; g.rskip0 = uL; g.rskipn = 2;
@@ -419,7 +435,7 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
             launch_bulk(c, g, nu - 2, nu - 2);
         }
         CU(cudaGetLastError());
-        b = bn; gn = gnn; sbase ^= 2;
+        b = bn; gn = gnn; sbase ^= gsz;
     }
     c->cur = nullptr;
     if (two) { CU(cudaEventRecord(c->ev_side, T)); CU(cudaStreamWaitEvent(S, c->ev_side, 0)); }
@@ -581,7 +597,7 @@ void fw_ctx_destroy(fw_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->edge_state) { fw_state_destroy(c->edge_state); c->edge_state = nullptr; }
-    for (int i = 0; i < 4; ++i) { c->Cp[i].release(); c->Rw[i].release(); c->NCp[i].release(); }
+    for (int i = 0; i < 16; ++i) { c->Cp[i].release(); c->Rw[i].release(); c->NCp[i].release(); }
     c->w_rate.release(); c->w_next.release(); c->w_mid.release(); c->w_csT.release(); c->w_rs.release();
     c->s_rate.release(); c->s_next.release(); c->s_mid.release(); c->s_csT.release(); c->s_rs.release();
     if (c->d_flag) cudaFree(c->d_flag);
@@ -1173,8 +1189,7 @@ int fw_shard_update_ex(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t
     fw::BulkArgs g;
     g.rate = rate_v; g.next = next_v; g.mid = nullptr; g.ld = ld; g.b0 = b0; g.row0 = row0 + v0;
     g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
-    g.CpT[0] = cp_v; g.NCp[0] = ncp_v; g.Rw[0] = d_Rw;
-    g.CpT[1] = nullptr; g.NCp[1] = nullptr; g.Rw[1] = nullptr;
+    for (int i = 0; i < fw::BULK_MAXNB; ++i) { g.CpT[i] = cp_v; g.NCp[i] = ncp_v; g.Rw[i] = d_Rw; }
     g.ldc = rows; g.ldw = n;
     g.row_lo = 0; g.rskip0 = (s0v == NOSKIP) ? NOSKIP : s0v / 64; g.rskipn = sn / 64;
     g.col_lo = 0; g.cskip0 = b0 / 64; g.cskipn = 2;
@@ -1236,7 +1251,7 @@ int fw_shard_update_pair(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64
     fw::BulkArgs g;
     g.rate = rate_v; g.next = next_v; g.mid = nullptr; g.ld = ld; g.b0 = b0; g.row0 = row0 + v0;
     g.ldc = rows; g.ldw = n;
-    for (int set = 0; set < 2; ++set) { g.CpT[set] = cp_v[set]; g.NCp[set] = ncp_v[set]; g.Rw[set] = Rws[set]; }
+    for (int i = 0; i < fw::BULK_MAXNB; ++i) { const int set = i < 2 ? i : 1; g.CpT[i] = cp_v[set]; g.NCp[i] = ncp_v[set]; g.Rw[i] = Rws[set]; }
     g.row_lo = 0; g.rskip0 = (s0v == NOSKIP) ? NOSKIP : s0v / 64; g.rskipn = sn / 64;
     for (int blk = 0; blk < 2; ++blk) {
         // column panel of block blk (its column strip is current: bulk of the previous pair / the strip launch below)

@@ -165,10 +165,12 @@ def test_device_resident_api(ctx):
 @pytest.mark.parametrize("knobs", [{"FW_FUSE_PAIRS": "2"}, {"FW_FUSE_PAIRS": "0"},
                                    {"FW_FUSE_PAIRS": "2", "FW_OVERLAP": "0"},
                                    {"FW_FUSE_PAIRS": "2", "FW_BULK_BAND": "3"},
-                                   {"FW_PANEL_NJ": "2"}, {"FW_PANEL_NJ": "2", "FW_FUSE_PAIRS": "2"}])
-@pytest.mark.parametrize("E,C", [(24, 16), (45, 16), (70, 10)])
+                                   {"FW_PANEL_NJ": "2"}, {"FW_PANEL_NJ": "2", "FW_FUSE_PAIRS": "2"},
+                                   {"FW_FUSE_GROUP": "4"}, {"FW_FUSE_GROUP": "4", "FW_OVERLAP": "0"},
+                                   {"FW_FUSE_GROUP": "8"}, {"FW_FUSE_GROUP": "1"}])
+@pytest.mark.parametrize("E,C", [(24, 16), (45, 16), (70, 10), (64, 16)])
 def test_schedule_variants(monkeypatch, E, C, knobs):
-    """n = 384, 720, 700: every schedule the large solves use (k-blocks in pairs, which by default
+    """n = 384, 720, 700, 1024: every schedule the large solves use (k-blocks in groups of 2 or 4, which by default
     starts at 48 k-blocks; side-stream look-ahead; raster bands; two panel jobs per half-warp, which by
     default starts at 9472 rows) must give the reference's bits.
     The knobs are read when a context first launches, so each case takes a fresh context."""
