@@ -26,7 +26,7 @@ SYMBOLS = (
     "fw_version", "fw_last_error", "fw_device_count", "fw_ctx_create", "fw_ctx_destroy",
     "fw_ctx_set_stream", "fw_ctx_last_launches", "fw_solve", "fw_solve_device", "fw_solve_batched",
     "fw_solve_batched_device", "fw_ctx_synchronize", "fw_ctx_set_profiling", "fw_ctx_phase_ms",
-    "fw_ctx_phase_spans", "fw_shard_validate", "fw_shard_pivot", "fw_shard_update", "fw_shard_update_ex", "fw_shard_update_pair",
+    "fw_ctx_phase_spans", "fw_shard_validate", "fw_shard_pivot", "fw_shard_update", "fw_shard_update_ex", "fw_shard_update_pair", "fw_shard_update_group",
     "fw_paths", "fw_paths_device", "fw_build_matrix_device", "fw_state_create", "fw_state_destroy",
     "fw_state_sync", "fw_state_optimum", "fw_state_download", "fw_solve_edges",
 )
@@ -81,6 +81,8 @@ def load():
     L.fw_shard_update_ex.argtypes = [vp, i32, i32, i32, i64, vp, vp, i32, vp, i32, i32]
     L.fw_shard_update_pair.restype = ctypes.c_int
     L.fw_shard_update_pair.argtypes = [vp, i32, i32, i32, i64, vp, vp, i32, vp, vp, i32, i32, i32]
+    L.fw_shard_update_group.restype = ctypes.c_int
+    L.fw_shard_update_group.argtypes = [vp, i32, i32, i32, i64, vp, vp, i32, i32, ctypes.POINTER(vp), i32, i32, i32]
     L.fw_paths.restype = ctypes.c_int
     L.fw_paths.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i64]
     L.fw_paths_device.restype = ctypes.c_int

@@ -1198,42 +1198,46 @@ int fw_shard_update_ex(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t
     return FW_OK;
 }
 
-int fw_shard_update_pair(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
-                         int32_t *d_next, int32_t b0, const double *d_Rw0, const double *d_Rw1, int32_t mode,
-                         int32_t lr0, int32_t lrn) {
-    constexpr int P2 = 2 * FW_B;
-    if (!c || !shard_args_ok(n, row0, rows, ld, d_rate, d_next, b0, d_Rw0) || !d_Rw1 || ((uintptr_t)d_Rw1 & 15))
-        return fail(FW_ERR_INVALID, "fw_shard_update_pair: bad argument (sizes must be multiples of 128, 16-byte aligned)");
-    if (row0 % P2 || rows % P2 || b0 % P2 || b0 + P2 > n)
-        return fail(FW_ERR_INVALID, "fw_shard_update_pair: row0, rows and b0 must be multiples of 256");
+int fw_shard_update_group(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
+                          int32_t *d_next, int32_t b0, int32_t nb, const double *const *d_Rw, int32_t mode,
+                          int32_t lr0, int32_t lrn) {
+    if (!c || !d_Rw || nb < 1 || nb > fw::BULK_MAXNB || !shard_args_ok(n, row0, rows, ld, d_rate, d_next, b0, d_Rw[0]))
+        return fail(FW_ERR_INVALID, "fw_shard_update_group: bad argument (sizes must be multiples of 128, 16-byte aligned)");
+    for (int i = 0; i < nb; ++i)
+        if (!d_Rw[i] || ((uintptr_t)d_Rw[i] & 15)) return fail(FW_ERR_INVALID, "fw_shard_update_group: bad panel pointer");
+    const int gw = nb * FW_B;                       // width of the group in rows / columns
+    if (b0 + gw > n) return fail(FW_ERR_INVALID, "fw_shard_update_group: the k-blocks run past n");
     if (mode < 0 || mode > 2 || (mode != 0 && (lr0 < 0 || lrn <= 0 || lr0 % FW_B || lrn % FW_B || lr0 + lrn > rows)))
-        return fail(FW_ERR_INVALID, "fw_shard_update_pair: bad mode / row range");
+        return fail(FW_ERR_INVALID, "fw_shard_update_group: bad mode / row range");
+    // the blocks' own rows, clipped to this shard (local rows [g0, g0 + gn))
+    int g0 = b0 - row0, g1 = b0 + gw - row0;
+    if (g0 < 0) g0 = 0;
+    if (g1 > rows) g1 = rows;
+    const int gn = g1 > g0 ? g1 - g0 : 0;
     std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaSetDevice(c->device));
     c->cur = nullptr;
     int rc;
     if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
-    for (int set = 0; set < 2; ++set) {
+    for (int set = 0; set < nb; ++set) {
         if ((rc = c->Cp[set].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
         if ((rc = c->NCp[set].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
     }
-    const bool owner = (b0 >= row0 && b0 < row0 + rows);
-    const int blk_r0 = owner ? b0 - row0 : -1;
     c->launches = 0;
     recycle_spans(c);
     // rows to process: the sub-shard [v0, v0 + vrows) minus one skip range [s0, s0 + sn)   (local rows)
     int v0 = 0, vrows = rows, s0 = NOSKIP, sn = 0;
     if (mode == 1) {
-        if (owner && lr0 < blk_r0 + P2 && blk_r0 < lr0 + lrn)
-            return fail(FW_ERR_INVALID, "fw_shard_update_pair: mode 1 rows overlap the pair's own rows");
+        if (gn > 0 && lr0 < g0 + gn && g0 < lr0 + lrn)
+            return fail(FW_ERR_INVALID, "fw_shard_update_group: mode 1 rows overlap the k-blocks' own rows");
         v0 = lr0; vrows = lrn;
     } else {
-        if (owner) { s0 = blk_r0; sn = P2; }
+        if (gn > 0) { s0 = g0; sn = gn; }
         if (mode == 2) {
-            if (!owner) { s0 = lr0; sn = lrn; }
-            else if (lr0 == blk_r0 + P2) { sn = P2 + lrn; }
-            else if (lr0 + lrn == blk_r0) { s0 = lr0; sn = P2 + lrn; }
-            else return fail(FW_ERR_INVALID, "fw_shard_update_pair: mode 2 needs the row range adjacent to the pair's rows");
+            if (gn == 0) { s0 = lr0; sn = lrn; }
+            else if (lr0 == g0 + gn) { sn = gn + lrn; }
+            else if (lr0 + lrn == g0) { s0 = lr0; sn = gn + lrn; }
+            else return fail(FW_ERR_INVALID, "fw_shard_update_group: mode 2 needs the row range adjacent to the k-blocks' rows");
         }
     }
     const int rows_out = vrows - sn;
@@ -1241,42 +1245,46 @@ int fw_shard_update_pair(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64
     double *rate_v = d_rate + (long long)v0 * ld;
     int32_t *next_v = d_next + (long long)v0 * ld;
     const int s0v = (s0 == NOSKIP) ? NOSKIP : s0 - v0;
-    const double *Rws[2] = {d_Rw0, d_Rw1};
-    double *cp_v[2];
-    int32_t *ncp_v[2];
-    for (int set = 0; set < 2; ++set) {
-        cp_v[set] = c->Cp[set].p + v0;                        // CpT[kk*ldc + i]
-        ncp_v[set] = c->NCp[set].p + (long long)v0 * FW_B;    // NCp[i*B + kk]
-    }
     fw::BulkArgs g;
     g.rate = rate_v; g.next = next_v; g.mid = nullptr; g.ld = ld; g.b0 = b0; g.row0 = row0 + v0;
     g.ldc = rows; g.ldw = n;
-    for (int i = 0; i < fw::BULK_MAXNB; ++i) { const int set = i < 2 ? i : 1; g.CpT[i] = cp_v[set]; g.NCp[i] = ncp_v[set]; g.Rw[i] = Rws[set]; }
+    for (int i = 0; i < fw::BULK_MAXNB; ++i) {
+        const int set = i < nb ? i : nb - 1;
+        g.CpT[i] = c->Cp[set].p + v0;                         // CpT[kk*ldc + i]
+        g.NCp[i] = c->NCp[set].p + (long long)v0 * FW_B;      // NCp[i*B + kk]
+        g.Rw[i] = d_Rw[set];
+    }
     g.row_lo = 0; g.rskip0 = (s0v == NOSKIP) ? NOSKIP : s0v / 64; g.rskipn = sn / 64;
-    for (int blk = 0; blk < 2; ++blk) {
-        // column panel of block blk (its column strip is current: bulk of the previous pair / the strip launch below)
+    g.half_r0 = NOSKIP;                             // no tile of these rows lies in a row strip of the group
+    for (int blk = 0; blk < nb; ++blk) {
+        if (blk > 0) {
+            // blocks 0 .. blk-1 on the column strip of block blk, so that its column panel can run
+            g.nb = blk; g.half_c0 = NOSKIP;
+            g.col_lo = (b0 + blk * FW_B) / 64; g.cskip0 = NOSKIP; g.cskipn = 0;
+            launch_bulk(c, g, 2, rows_out / 64);
+        }
         fw::PanelArgs p;
         p.rate = rate_v; p.next = next_v; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
         p.ld = ld; p.npad = n; p.b0 = b0 + blk * FW_B; p.rows = vrows; p.blk_r0 = NOSKIP; p.skip_r0 = s0v; p.skipn = sn;
-        p.Cp = cp_v[blk]; p.ldc = rows; p.NCp = ncp_v[blk]; p.Rw = const_cast<double *>(Rws[blk]); p.ldw = n;
-        {
-            PhaseTimer pt(c, 1);
-            launch_panel<true>(c, p, rows_out, false, c->stream);
-        }
-        if (blk == 0) {
-            // the first block's 128 steps on the column strip of the second, so that its column panel can run
-            g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
-            g.col_lo = (b0 + FW_B) / 64; g.cskip0 = NOSKIP; g.cskipn = 0;
-            launch_bulk(c, g, 2, rows_out / 64);
-        }
+        p.Cp = const_cast<double *>(g.CpT[blk]); p.ldc = rows; p.NCp = const_cast<int32_t *>(g.NCp[blk]);
+        p.Rw = const_cast<double *>(d_Rw[blk]); p.ldw = n;
+        PhaseTimer pt(c, 1);
+        launch_panel<true>(c, p, rows_out, false, c->stream);
     }
-    // both blocks' steps for every other tile from one load; the first block's own column strip took its
-    // first 128 steps in the column panel and starts at the second block's
-    g.nb = 2; g.half_r0 = NOSKIP; g.half_c0 = b0 / 64;
-    g.col_lo = 0; g.cskip0 = (b0 + FW_B) / 64; g.cskipn = 2;
+    // all nb blocks for every other tile from one load; the column strip of block i < nb-1 took blocks 0..i in
+    // the strip launches and its column panel and starts at block i+1; the last block's strip is complete
+    g.nb = nb; g.half_c0 = (nb > 1) ? b0 / 64 : NOSKIP;
+    g.col_lo = 0; g.cskip0 = (b0 + (nb - 1) * FW_B) / 64; g.cskipn = 2;
     launch_bulk(c, g, n / 64 - 2, rows_out / 64);
     CU(cudaGetLastError());
     return FW_OK;
+}
+
+int fw_shard_update_pair(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
+                         int32_t *d_next, int32_t b0, const double *d_Rw0, const double *d_Rw1, int32_t mode,
+                         int32_t lr0, int32_t lrn) {
+    const double *rw[2] = {d_Rw0, d_Rw1};
+    return fw_shard_update_group(c, n, row0, rows, ld, d_rate, d_next, b0, 2, rw, mode, lr0, lrn);
 }
 
 int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,

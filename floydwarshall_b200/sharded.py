@@ -29,6 +29,7 @@ from . import _lib
 
 B = _lib.FW_TILE
 LOOKAHEAD = os.environ.get("FW_LOOKAHEAD", "1") != "0"   # pivot-panel look-ahead on a second stream
+MAX_GROUP = 8                                            # most k-blocks per fused bulk launch (fw::BULK_MAXNB)
 
 
 def shard_rows(n: int, world: int) -> int:
@@ -90,53 +91,56 @@ def run_schedule_lookahead(backend, n: int, rank: int, world: int, rt) -> None:
         rt.a_done()
 
 
-def run_schedule_lookahead_pairs(backend, n: int, rank: int, world: int, rt) -> None:
-    """run_schedule_lookahead with the k-blocks taken in PAIRS (p = blocks 2p, 2p+1), so that the bulk
-    kernel loads every tile of the shard once per 256 steps (backend.update_pair).  A pair never straddles
-    two ranks (rows per rank is a multiple of 2B).  Per pair its owner factors both blocks on the look-ahead
-    lane -- pivot(2p), broadcast, the 128 rows of block 2p+1 take block 2p, pivot(2p+1), broadcast -- after
-    bringing the pair's 256 rows up to date with the previous pair; the main lane gives every other local
-    row both blocks in one update_pair, and the owner's rows of block 2p take block 2p+1 on their own.
-    Panel buffers: pair p uses backend.Rw buffers 2*(p&1) and 2*(p&1)+1."""
+def run_schedule_lookahead_groups(backend, n: int, rank: int, world: int, rt, G: int = 2) -> None:
+    """run_schedule_lookahead with the k-blocks taken in GROUPS of G consecutive blocks, so that the bulk
+    kernel loads every tile of the shard once per G*128 steps (backend.update_group).  A group never
+    straddles two ranks (rows per rank is a multiple of G*B).  Per group its owner factors the G blocks on
+    the look-ahead lane -- for block j: its 128 rows take the group's blocks 0..j-1, pivot, broadcast --
+    after bringing the group's rows up to date with the previous group; the main lane gives every other
+    local row all G blocks in one update_group, and the owner's rows of block i take the blocks after i on
+    their own.  Panel buffers: group p uses backend.Rw buffers G*(p&1) .. G*(p&1)+G-1."""
     rows = shard_rows(n, world)
-    if rows % (2 * B) != 0:
-        raise ValueError(f"pairs need rows per rank ({rows}) to be a multiple of {2 * B}")
-    npair = n // (2 * B)
+    if rows % (G * B) != 0:
+        raise ValueError(f"groups of {G} need rows per rank ({rows}) to be a multiple of {G * B}")
+    ngrp = n // (G * B)
 
     def factor(p):
-        b0, s = 2 * p * B, 2 * (p & 1)
+        b0, s = G * p * B, G * (p & 1)
         owner = b0 // rows
-        if rank == owner:
-            backend.pivot(b0, s)
-        if world > 1:
-            rt.bcast(s, owner)
-        if rank == owner:
-            backend.update(b0, s, 1, (b0 + B) - rank * rows)     # rows of the second block take the first
-            backend.pivot(b0 + B, s + 1)
-        if world > 1:
-            rt.bcast(s + 1, owner)
+        for j in range(G):
+            if rank == owner:
+                if j > 0:                                      # rows of block j take blocks 0..j-1 of the group
+                    backend.update_group(b0, j, s, 1, (b0 + j * B) - rank * rows, B)
+                backend.pivot(b0 + j * B, s + j)
+            if world > 1:
+                rt.bcast(s + j, owner)
 
     with rt.lane_b():
         factor(0)
     rt.b_done()
-    for p in range(npair):
-        b0, s = 2 * p * B, 2 * (p & 1)
-        nxt = p + 1 < npair
+    for p in range(ngrp):
+        b0, s = G * p * B, G * (p & 1)
+        nxt = p + 1 < ngrp
         own = (b0 // rows == rank)
-        own_next = nxt and ((b0 + 2 * B) // rows == rank)
-        lr_next = (b0 + 2 * B) - rank * rows
-        rt.wait_b_done()                      # both panels of pair p are here
+        own_next = nxt and ((b0 + G * B) // rows == rank)
+        lr_next = (b0 + G * B) - rank * rows
+        rt.wait_b_done()                      # all panels of group p are here
         if nxt:
             with rt.lane_b():
-                rt.wait_a_done()              # pair p-1 is finished: the rows of pair p+1 and its buffers are free
+                rt.wait_a_done()              # group p-1 is finished: the rows of group p+1 and its buffers are free
                 if own_next:
-                    backend.update_pair(b0, s, 1, lr_next, 2 * B)   # only the next pair's 256 rows
+                    backend.update_group(b0, G, s, 1, lr_next, G * B)     # only the next group's rows
                 factor(p + 1)
                 rt.b_done()
-        backend.update_pair(b0, s, 2 if own_next else 0, lr_next if own_next else 0, 2 * B if own_next else 0)
+        backend.update_group(b0, G, s, 2 if own_next else 0, lr_next if own_next else 0, G * B if own_next else 0)
         if own:
-            backend.update(b0 + B, s + 1, 1, b0 - rank * rows)       # the first block's rows take the second
+            for i in range(G - 1):            # the rows of block i take the blocks after it
+                backend.update_group(b0 + (i + 1) * B, G - 1 - i, s + i + 1, 1, (b0 + i * B) - rank * rows, B)
         rt.a_done()
+
+
+def run_schedule_lookahead_pairs(backend, n: int, rank: int, world: int, rt) -> None:
+    run_schedule_lookahead_groups(backend, n, rank, world, rt, 2)
 
 
 class SerialRuntime:
@@ -228,7 +232,7 @@ class GpuShardBackend:
         assert rate_t.shape[1] == n and rate_t.dtype == torch.float64 and next_t.dtype == torch.int32
         self.ctx, self.n, self.row0, self.rows = ctx, n, row0, rate_t.shape[0]
         self.rate, self.next = rate_t, next_t
-        self.Rw2 = [torch.empty((B, n), dtype=torch.float64, device=rate_t.device) for _ in range(4)]
+        self.Rw2 = [torch.empty((B, n), dtype=torch.float64, device=rate_t.device) for _ in range(2 * MAX_GROUP)]
         self.Rw = self.Rw2[0]
         self.L = _lib.load()
         self.launches = 0
@@ -251,14 +255,30 @@ class GpuShardBackend:
                                              mode, lr0))
         self.launches += self.ctx.last_launches
 
-    def update_pair(self, b0: int, buf: int = 0, mode: int = 0, lr0: int = 0, lrn: int = 0):
-        _lib.check(self.L.fw_shard_update_pair(self.ctx.handle, self.n, self.row0, self.rows, self.n,
-                                               self._p(self.rate), self._p(self.next), b0, self._p(self.Rw2[buf]),
-                                               self._p(self.Rw2[buf + 1]), mode, lr0, lrn))
+    def update_group(self, b0: int, nb: int, buf: int = 0, mode: int = 0, lr0: int = 0, lrn: int = 0):
+        """nb consecutive k-blocks from b0 with the panels Rw2[buf .. buf+nb-1] (fw_shard_update_group)."""
+        arr = (ctypes.c_void_p * nb)(*[self.Rw2[buf + i].data_ptr() for i in range(nb)])
+        _lib.check(self.L.fw_shard_update_group(self.ctx.handle, self.n, self.row0, self.rows, self.n,
+                                                self._p(self.rate), self._p(self.next), b0, nb, arr, mode, lr0, lrn))
         self.launches += self.ctx.last_launches
 
+    def update_pair(self, b0: int, buf: int = 0, mode: int = 0, lr0: int = 0, lrn: int = 0):
+        self.update_group(b0, 2, buf, mode, lr0, lrn)
 
-PAIRS = os.environ.get("FW_SHARD_PAIRS", "1") != "0"     # k-blocks in pairs when the shard geometry allows it
+
+PAIRS = os.environ.get("FW_SHARD_PAIRS", "1") != "0"     # k-blocks in groups when the shard geometry allows it
+GROUP = int(os.environ.get("FW_SHARD_GROUP", "0"))       # 0: the largest of 8 / 4 / 2 that divides the rows per rank
+
+
+def shard_group(n: int, world: int) -> int:
+    """k-blocks per fused bulk launch of the sharded solve (1 = the plain per-block schedule)."""
+    rows = shard_rows(n, world)
+    if not PAIRS:
+        return 1
+    for g in ((GROUP,) if GROUP in (1, 2, 4, 8) else (8, 4, 2)):
+        if g == 1 or (rows % (g * B) == 0 and n // (g * B) >= 2):
+            return g
+    return 1
 
 
 def solve_shard(backend, n: int, rank: int, world: int, lookahead: bool = True):
@@ -266,8 +286,9 @@ def solve_shard(backend, n: int, rank: int, world: int, lookahead: bool = True):
     import torch.distributed as dist
     if lookahead:
         rt = TorchRuntime(backend, world)
-        if PAIRS and shard_rows(n, world) % (2 * B) == 0:
-            run_schedule_lookahead_pairs(backend, n, rank, world, rt)
+        G = shard_group(n, world)
+        if G > 1:
+            run_schedule_lookahead_groups(backend, n, rank, world, rt, G)
         else:
             run_schedule_lookahead(backend, n, rank, world, rt)
         rt.finish()
@@ -455,7 +476,7 @@ def bench_main(args, METRIC, UNIT, SEED, workload_n, workload_name, ClockSampler
             "config": {"workload": workload_name(n), "n": n, "seed": SEED + 1, "k_block": B,
                        "sharding": f"row blocks of {rows} rows per rank; per-k-block NCCL broadcast of the "
                                    f"128 x {n} fp64 pivot-row snapshot panel ({B * n * 8 / 2**20:.0f} MiB)",
-                       "lookahead": LOOKAHEAD, "k_blocks_in_pairs": bool(LOOKAHEAD and PAIRS and rows % (2 * B) == 0),
+                       "lookahead": LOOKAHEAD, "k_blocks_per_bulk_launch": (shard_group(n, world) if LOOKAHEAD else 1),
                        "l2": "per-rank inputs are far larger than the 126 MB L2; no flush needed",
                        "check": check},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches.item()),

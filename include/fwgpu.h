@@ -200,6 +200,17 @@ int fw_shard_update_ex(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64
 int fw_shard_update_pair(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
                          double *d_rate, int32_t *d_next, int32_t b0, const double *d_Rw0,
                          const double *d_Rw1, int32_t mode, int32_t lr0, int32_t lrn);
+/* nb (1..8) CONSECUTIVE k-blocks b0, b0+128, ... in one call (fw_shard_update_pair is nb = 2): for each
+ * block in turn its column panel, preceded by one fused launch that brings the block's column strip up
+ * to date with the earlier blocks of the call, then one fused bulk launch of all nb blocks.  d_Rw[i] is
+ * the row-snapshot panel of block i (HOST array of nb device pointers).  Rows: mode 0 = every local row
+ * outside [b0, b0 + nb*128); mode 1 = ONLY the lrn local rows starting at lr0 (any rows that do not
+ * intersect the blocks' own); mode 2 = mode 0 minus those rows (adjacent to the blocks' rows when the
+ * shard owns them).  The blocks' own rows are the owner's business, before and after the broadcasts
+ * (floydwarshall_b200/sharded.py: run_schedule_lookahead_groups). */
+int fw_shard_update_group(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
+                          double *d_rate, int32_t *d_next, int32_t b0, int32_t nb,
+                          const double *const *d_Rw, int32_t mode, int32_t lr0, int32_t lrn);
 
 /* Block until everything queued on the context's stream has finished and
  * report any asynchronous failure (incl. FW_ERR_DOMAIN of *_device calls). */

@@ -10,7 +10,7 @@ class NumpyShardBackend:
     def __init__(self, n, row0, rate, nxt, block=B):
         self.n, self.row0, self.rows, self.B = n, row0, rate.shape[0], block
         self.rate, self.next = rate, nxt
-        self.Rw2 = [np.zeros((block, n)) for _ in range(4)]
+        self.Rw2 = [np.zeros((block, n)) for _ in range(16)]
         self.Rw = self.Rw2[0]
         self.Cp = np.zeros((self.rows, block))
         self.NCp = np.zeros((self.rows, block), dtype=np.int32)
@@ -100,9 +100,12 @@ class NumpyShardBackend:
         self.rate[np.ix_(ridx, cidx)] = Rb
         self.next[np.ix_(ridx, cidx)] = Xb
 
-    def update_pair(self, b0, buf=0, mode=0, lr0=0, lrn=0):
-        """k-blocks b0 and b0+B (panels Rw2[buf], Rw2[buf+1]) on every local row outside the PAIR's own
-        rows (modes as in update): by definition the two single-block updates one after the other."""
+    def update_group(self, b0, nb, buf=0, mode=0, lr0=0, lrn=0):
+        """k-blocks b0, b0+B, ... (panels Rw2[buf..buf+nb-1]) on every local row outside the blocks' own rows
+        (modes as in update): by definition the single-block updates one after the other."""
         B_ = self.B
-        self.update(b0, buf, mode, lr0, lrn, extra_skip=(b0 + B_ - self.row0, B_))
-        self.update(b0 + B_, buf + 1, mode, lr0, lrn, extra_skip=(b0 - self.row0, B_))
+        for i in range(nb):
+            self.update(b0 + i * B_, buf + i, mode, lr0, lrn if lrn else None, extra_skip=(b0 - self.row0, nb * B_))
+
+    def update_pair(self, b0, buf=0, mode=0, lr0=0, lrn=0):
+        self.update_group(b0, 2, buf, mode, lr0, lrn)

@@ -70,18 +70,21 @@ def test_virtual_ranks_on_one_gpu(world, E, C, mode, lookahead):
         c.close()
 
 
-@pytest.mark.parametrize("world,E,C,mode", [(1, 32, 16, "consistent"), (2, 32, 16, "arbitrage"),
-                                            (2, 64, 16, "consistent"), (4, 64, 16, "pow2")])
-def test_virtual_ranks_pairs_on_one_gpu(world, E, C, mode):
-    """The call sequence of sharded.run_schedule_lookahead_pairs (fw_shard_update_pair: two k-blocks per
-    bulk launch), serialised on one stream; n = 512 / 1024 so that a rank owns one or two whole pairs."""
+@pytest.mark.parametrize("G,world,E,C,mode", [(2, 1, 32, 16, "consistent"), (2, 2, 32, 16, "arbitrage"),
+                                              (2, 2, 64, 16, "consistent"), (2, 4, 64, 16, "pow2"),
+                                              (4, 1, 64, 16, "arbitrage"), (4, 2, 64, 16, "consistent"),
+                                              (4, 2, 128, 16, "consistent"), (8, 1, 128, 16, "consistent"),
+                                              (8, 2, 128, 16, "arbitrage")])
+def test_virtual_ranks_groups_on_one_gpu(G, world, E, C, mode):
+    """The call sequence of sharded.run_schedule_lookahead_groups (fw_shard_update_group: G k-blocks per
+    bulk launch), serialised on one stream; n = 512 / 1024 / 2048 so that a rank owns one or two groups."""
     import torch
     n = E * C
     B = sharded.B
     rate, nxt = graphs.exchange_graph(E, C, seed=33, density=0.7, mode=mode)
     ref = O.solve_dense(rate, nxt, threads=0)
     rows = sharded.shard_rows(n, world)
-    assert rows % (2 * B) == 0
+    assert rows % (G * B) == 0
     ctxs = [_lib.Context(0) for _ in range(world)]
     stream = torch.cuda.current_stream().cuda_stream
     bes = []
@@ -99,29 +102,30 @@ def test_virtual_ranks_pairs_on_one_gpu(world, E, C, mode):
                 bes[r].Rw2[buf].copy_(bes[owner].Rw2[buf])
 
     def factor(p):
-        b0, s = 2 * p * B, 2 * (p & 1)
+        b0, s = G * p * B, G * (p & 1)
         ow = b0 // rows
-        bes[ow].pivot(b0, s)
-        share(s, ow)
-        bes[ow].update(b0, s, 1, (b0 + B) - ow * rows)
-        bes[ow].pivot(b0 + B, s + 1)
-        share(s + 1, ow)
+        for j in range(G):
+            if j > 0:
+                bes[ow].update_group(b0, j, s, 1, (b0 + j * B) - ow * rows, B)
+            bes[ow].pivot(b0 + j * B, s + j)
+            share(s + j, ow)
 
-    npair = n // (2 * B)
+    ngrp = n // (G * B)
     factor(0)
-    for p in range(npair):
-        b0, s = 2 * p * B, 2 * (p & 1)
-        on = (b0 + 2 * B) // rows if p + 1 < npair else -1
+    for p in range(ngrp):
+        b0, s = G * p * B, G * (p & 1)
+        on = (b0 + G * B) // rows if p + 1 < ngrp else -1
         if on >= 0:
-            bes[on].update_pair(b0, s, 1, (b0 + 2 * B) - on * rows, 2 * B)
+            bes[on].update_group(b0, G, s, 1, (b0 + G * B) - on * rows, G * B)
             factor(p + 1)
         for r in range(world):
             if r == on:
-                bes[r].update_pair(b0, s, 2, (b0 + 2 * B) - r * rows, 2 * B)
+                bes[r].update_group(b0, G, s, 2, (b0 + G * B) - r * rows, G * B)
             else:
-                bes[r].update_pair(b0, s, 0, 0, 0)
+                bes[r].update_group(b0, G, s, 0, 0, 0)
         ow = b0 // rows
-        bes[ow].update(b0 + B, s + 1, 1, b0 - ow * rows)
+        for i in range(G - 1):
+            bes[ow].update_group(b0 + (i + 1) * B, G - 1 - i, s + i + 1, 1, (b0 + i * B) - ow * rows, B)
     torch.cuda.synchronize()
     got_r = np.concatenate([be.rate.cpu().numpy() for be in bes])
     got_x = np.concatenate([be.next.cpu().numpy() for be in bes])

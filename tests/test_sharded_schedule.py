@@ -37,8 +37,9 @@ def _worker(rank, world, port, n, block, mode, out_dir, lookahead=False):
 
     sharded.B = block      # the schedule is block-size agnostic; shrink it so the test is fast
     try:
-        if lookahead == "pairs":
-            sharded.run_schedule_lookahead_pairs(be, n, rank, world, sharded.SerialRuntime(bcast2))
+        if isinstance(lookahead, str):
+            sharded.run_schedule_lookahead_groups(be, n, rank, world, sharded.SerialRuntime(bcast2),
+                                                  {"pairs": 2, "quads": 4}[lookahead])
         elif lookahead:
             sharded.run_schedule_lookahead(be, n, rank, world, sharded.SerialRuntime(bcast2))
         else:
@@ -52,13 +53,13 @@ def _worker(rank, world, port, n, block, mode, out_dir, lookahead=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("lookahead", [False, True, "pairs"])
+@pytest.mark.parametrize("lookahead", [False, True, "pairs", "quads"])
 @pytest.mark.parametrize("mode", ["consistent", "arbitrage"])
 def test_two_rank_schedule_matches_oracle(tmp_path, mode, lookahead):
     from floydwarshall_b200 import graphs
     from oracle import fw_oracle as O
     n, block, world = 64, 8, 2
-    port = 29500 + (os.getpid() % 2000) + {False: 0, True: 7, "pairs": 13}[lookahead]
+    port = 29500 + (os.getpid() % 2000) + {False: 0, True: 7, "pairs": 13, "quads": 19}[lookahead]
     mp.spawn(_worker, args=(world, port, n, block, mode, str(tmp_path), lookahead), nprocs=world, join=True)
     rate, nxt = graphs.exchange_graph(n // 8, 8, seed=21, density=0.8, mode=mode)
     ref = O.solve_dense(rate, nxt)
