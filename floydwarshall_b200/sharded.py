@@ -267,7 +267,10 @@ class GpuShardBackend:
 
 
 PAIRS = os.environ.get("FW_SHARD_PAIRS", "1") != "0"     # k-blocks in groups when the shard geometry allows it
-GROUP = int(os.environ.get("FW_SHARD_GROUP", "0"))       # 0: the largest of 8 / 4 / 2 that divides the rows per rank
+# k-blocks per fused bulk launch of the sharded solve.  Measured at 8 GPUs, N=65536: pairs 4513 ms, groups of 8
+# 4597 ms (unpaired 4906 ms): the owner brings its group's own rows through the group in 128-row slices on the
+# look-ahead lane, and with 8 blocks per group those small launches outweigh the saved tile loads.
+GROUP = int(os.environ.get("FW_SHARD_GROUP", "2"))
 
 
 def shard_group(n: int, world: int) -> int:
@@ -275,7 +278,7 @@ def shard_group(n: int, world: int) -> int:
     rows = shard_rows(n, world)
     if not PAIRS:
         return 1
-    for g in ((GROUP,) if GROUP in (1, 2, 4, 8) else (8, 4, 2)):
+    for g in ((GROUP, 2) if GROUP in (1, 2, 4, 8) else (8, 4, 2)):
         if g == 1 or (rows % (g * B) == 0 and n // (g * B) >= 2):
             return g
     return 1
