@@ -33,7 +33,12 @@
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
+#ifdef _OPENMP
 #include <omp.h>
+#else  /* single-threaded build (no OpenMP runtime available) */
+static int omp_get_max_threads(void) { return 1; }
+static void omp_set_num_threads(int n) { (void)n; }
+#endif
 #endif
 
 /*
