@@ -280,16 +280,23 @@ def run_ours(args):
         achieved = 2.0 * bulk_relax_total / (phase_ms[3] * 1e-3) / 1e12   # algorithmic FLOPs: 1 mul + 1 compare
     else:
         bulk_ms, achieved = None, None
+    # k-blocks per fused bulk launch: the library's size-based policy (fwgpu.cu, solve_blocked) unless forced
+    nblk = npad // 128
+    group = int(os.environ.get("FW_FUSE_GROUP", "0")) or (8 if nblk >= 128 else (4 if nblk >= 48 else 1))
     traffic = None
+    traffic_note = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("fw_bulk_kernel_dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("fw_bulk_kernel_dram_bytes_per_launch")
+            traffic_note = tj.get("_schedule_note")
         except Exception:  # noqa: BLE001
             traffic = None
     roofline = {
         "bound": "fp64", "kernel": "fw_bulk_kernel", "achieved": achieved, "peak": peak_tflops,
         "unit": "TFLOP/s", "frac": (achieved / peak_tflops) if achieved else None, "traffic": traffic,
+        "traffic_note": traffic_note,
         "peak_source": peak_src, "avg_launch_ms": bulk_ms, "launches_per_step": phase_cnt[3],
         "algorithmic_flops_per_launch": 2.0 * bulk_relax,
         "share_of_step": (phase_ms[3] / sum(phase_ms)) if sum(phase_ms) > 0 else None,
@@ -298,8 +305,9 @@ def run_ours(args):
                 "the side stream while the main stream's bulk launch is busy, so the spans overlap and their sum "
                 "can exceed the step time (achieved is the conservative figure, whole_solve_tflops = 2 N^3 / t)",
         "phase_ms": {"tile": phase_ms[0], "col_panel": phase_ms[1], "row_panel": phase_ms[2], "bulk": phase_ms[3]},
-        "hbm_side": {"algorithmic_bytes_per_solve": (npad // 256) * float(npad - 128) ** 2 * 8,
-                     "note": "bulk reads every entry once per PAIR of k-blocks (8 B) and writes only replaced "
+        "hbm_side": {"k_blocks_per_fused_launch": group,
+                     "algorithmic_bytes_per_solve": (npad // (128 * group)) * float(npad - 128) ** 2 * 8,
+                     "note": "bulk reads every entry once per GROUP of k-blocks (8 B) and writes only replaced "
                              "entries; launches of different sizes (strips / rest) are averaged"},
     }
 
