@@ -74,3 +74,11 @@ def test_shard_rows_validation():
     assert sharded.shard_rows(65536, 8) == 8192
     with pytest.raises(ValueError):
         sharded.shard_rows(1000, 2)
+
+
+def test_shard_group_policy():
+    """Pairs by default wherever a pair never straddles two ranks; the plain per-block schedule otherwise."""
+    from floydwarshall_b200 import sharded
+    assert sharded.shard_group(65536, 8) == 2 and sharded.shard_group(65536, 2) == 2
+    assert sharded.shard_group(1024, 8) == 1          # 128 rows per rank: no room for a pair
+    assert sharded.shard_group(256, 1) == 1           # a single pair: nothing to look ahead to
