@@ -29,6 +29,8 @@ SYMBOLS = (
     "fw_ctx_phase_spans", "fw_shard_validate", "fw_shard_pivot", "fw_shard_update", "fw_shard_update_ex", "fw_shard_update_pair", "fw_shard_update_group",
     "fw_paths", "fw_paths_device", "fw_build_matrix_device", "fw_state_create", "fw_state_destroy",
     "fw_state_sync", "fw_state_optimum", "fw_state_download", "fw_solve_edges",
+    "fw_ctx_last_error", "fw_solve_device_range", "fw_ctx_set_row_snapshot_sink",
+    "fw_tables_create", "fw_tables_destroy", "fw_tables_paths",
 )
 
 
@@ -102,6 +104,18 @@ def load():
     L.fw_state_download.argtypes = [vp, vp, vp]
     L.fw_solve_edges.restype = ctypes.c_int
     L.fw_solve_edges.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.fw_ctx_last_error.restype = ctypes.c_char_p
+    L.fw_ctx_last_error.argtypes = [vp]
+    L.fw_solve_device_range.restype = ctypes.c_int
+    L.fw_solve_device_range.argtypes = [vp, i32, i64, vp, vp, vp, vp, vp, i32, i32]
+    L.fw_ctx_set_row_snapshot_sink.restype = ctypes.c_int
+    L.fw_ctx_set_row_snapshot_sink.argtypes = [vp, vp, i64]
+    L.fw_tables_create.restype = ctypes.c_int
+    L.fw_tables_create.argtypes = [vp, i32, vp, vp, vp, vp, ctypes.POINTER(vp)]
+    L.fw_tables_destroy.restype = None
+    L.fw_tables_destroy.argtypes = [vp]
+    L.fw_tables_paths.restype = ctypes.c_int
+    L.fw_tables_paths.argtypes = [vp, i32, vp, vp, vp, i64]
     L.fw_solve.restype = ctypes.c_int
     L.fw_solve.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.fw_solve_device.restype = ctypes.c_int
@@ -114,9 +128,13 @@ def load():
     return L
 
 
-def check(rc: int):
+def check(rc: int, ctx_handle=None):
+    """Raise FwError for a non-zero status; the text comes from the context the call was made on
+    when its handle is given, else from this OS thread's last error."""
     if rc != FW_OK:
-        raise FwError(rc, load().fw_last_error().decode("utf-8", "replace"))
+        L = load()
+        msg = L.fw_ctx_last_error(ctx_handle) if ctx_handle else L.fw_last_error()   # Python stays on one OS thread
+        raise FwError(rc, (msg or b"").decode("utf-8", "replace"))
 
 
 class Context:

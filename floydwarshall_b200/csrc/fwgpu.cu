@@ -14,6 +14,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <new>
 #include <string>
@@ -21,6 +23,7 @@
 #include <vector>
 
 #include "../../include/fwgpu.h"
+struct fw_ctx;
 #include "fw_bulk.cuh"
 #include "fw_common.cuh"
 #include "fw_panel.cuh"
@@ -31,16 +34,29 @@ static_assert(FW_B == FW_TILE, "kernel block size and public tile size must agre
 
 namespace {
 
+// Error text: kept per OS thread (fw_last_error) AND per context (fw_ctx_last_error).  A GHC `safe` foreign
+// call and the fw_last_error call after it may run on different OS threads, so bindings read the
+// context's copy; every entry point names the context it works for with an ErrScope.
 thread_local std::string g_err;
+thread_local fw_ctx *g_err_ctx = nullptr;
+void note_ctx_error(fw_ctx *c, const std::string &msg);
 
 int fail(int code, const std::string &msg) {
     g_err = msg;
+    note_ctx_error(g_err_ctx, msg);
     return code;
 }
 int cuda_fail(cudaError_t e, const char *what) {
     g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    note_ctx_error(g_err_ctx, g_err);
     return (e == cudaErrorMemoryAllocation) ? FW_ERR_NOMEM : FW_ERR_CUDA;
 }
+#define FW_ENTER(c) ErrScope es__(c); std::lock_guard<std::recursive_mutex> lk__((c)->mu)
+struct ErrScope {
+    fw_ctx *prev;
+    explicit ErrScope(fw_ctx *c) : prev(g_err_ctx) { g_err_ctx = c; }
+    ~ErrScope() { g_err_ctx = prev; }
+};
 #define CU(call)                                                   \
     do {                                                           \
         cudaError_t e__ = (call);                                  \
@@ -131,12 +147,40 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+template <typename T>
+struct PinnedBuf {       // pinned (and mapped) host memory, grown on demand
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return FW_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc((void **)&p, n * sizeof(T), cudaHostAllocMapped);
+        if (e != cudaSuccess) { p = nullptr; return cuda_fail(e, "cudaHostAlloc"); }
+        cap = n;
+        return FW_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 }  // namespace
+
+
+// scratch of the path entry points, pooled per context (no cudaMalloc / cudaFree per call)
+struct fw_path_scratch {
+    DevBuf<int32_t> q, verts;
+    DevBuf<long long> len, off;
+    DevBuf<unsigned long long> gstack;
+    PinnedBuf<long long> h_len;
+    PinnedBuf<unsigned char> h_opt;
+    void release() { q.release(); verts.release(); len.release(); off.release(); gstack.release(); h_len.release(); h_opt.release(); }
+};
 
 struct fw_state;
 struct fw_ctx {
     int device = 0;
     fw_state *edge_state = nullptr;   // cached device state of fw_solve_edges (buffers reused across calls)
+    struct fw_path_scratch *pscratch = nullptr;   // pooled scratch of the path entry points
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t side_stream = nullptr;   // high priority: pivot phases of the NEXT k-blocks overlap the bulk kernel
@@ -144,7 +188,11 @@ struct fw_ctx {
     cudaEvent_t ev_main = nullptr, ev_side = nullptr;
     bool overlap = true;                  // knob FW_OVERLAP=0: everything on one stream
     cudaStream_t stream = nullptr;
-    std::mutex mu;
+    // A context serialises its own calls (include/fwgpu.h).  Recursive: composite entry points
+    // (fw_solve_edges, fw_solve_batched, fw_paths, fw_state_optimum) hold it across the calls they make.
+    std::recursive_mutex mu;
+    std::mutex err_mu;
+    std::string err, err_ret;      // text of the last failure on this context (fw_ctx_last_error)
     int64_t launches = 0;
     // snapshot panels
     DevBuf<double> Cp[16], Rw[16];   // panel sets: k-blocks go in groups of up to 8, and the next group is factored ahead
@@ -161,6 +209,9 @@ struct fw_ctx {
     int *d_flag = nullptr;
     int *h_flag = nullptr;
     bool attrs_set = false;
+    // verification hook (fw_ctx_set_row_snapshot_sink): every k-block's row-snapshot panel is also copied here
+    double *snap_sink = nullptr;
+    long long snap_ld = 0;
     int bulk_cq = 2;       // fw_bulk_kernel tile width / 32 (2: 8x4 micro-tile, 4: 8x8); knob FW_BULK_CQ
     int bulk_band = 64;    // tile columns per raster band of fw_bulk_kernel (L2 locality); knob FW_BULK_BAND
     // optional per-phase timing (CUDA events on the launching stream)
@@ -171,6 +222,14 @@ struct fw_ctx {
 };
 
 namespace {
+
+extern std::atomic<fw_ctx *> g_default;
+void note_ctx_error(fw_ctx *c, const std::string &msg) {
+    if (!c) c = g_default.load();     // calls made with ctx == NULL belong to the default context
+    if (!c) return;
+    std::lock_guard<std::mutex> lk(c->err_mu);
+    c->err = msg;
+}
 
 int set_kernel_attrs(fw_ctx *c) {
     if (c->attrs_set) return FW_OK;
@@ -327,6 +386,10 @@ int launch_pivot_phases(fw_ctx *c, int npad, long long ld, double *rate, int32_t
         }
     }
     CU(cudaGetLastError());
+    if (c->snap_sink)   // rows b0 .. b0+127 as their own steps began (the pivot entry itself is exported as 0.0)
+        CU(cudaMemcpy2DAsync(c->snap_sink + (long long)b0 * c->snap_ld, (size_t)c->snap_ld * 8, c->Rw[set].p,
+                             (size_t)npad * 8, (size_t)npad * 8, FW_B, cudaMemcpyDeviceToDevice,
+                             (c->cur ? c->cur : c->stream)));
     return FW_OK;
 }
 
@@ -347,10 +410,11 @@ int launch_pivot_phases(fw_ctx *c, int npad, long long ld, double *rate, int32_t
 // strips of the group's last block are complete and left out.  The order of relaxations seen by every
 // entry is unchanged (ascending k), so results are identical to the plain loop.
 int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next, int32_t *mid,
-                  int32_t *csT, int32_t *rs) {
+                  int32_t *csT, int32_t *rs, int kb0 = 0, int kb1 = -1) {
     constexpr int GMAX = fw::BULK_MAXNB;
     int rc;
     const int nblk = npad / FW_B;
+    if (kb1 < 0) kb1 = nblk;            // k-blocks [kb0, kb1) only (fw_solve_device_range); the group size follows the full solve
     const int nu = npad / 64;                 // 64-row / 64-column units
     // grouping splits every bulk launch in three and adds strip launches; below ~48 k-blocks the extra
     // launches cost more than the saved tile loads (N=1024: 2.26 ms ungrouped vs 2.50 ms in pairs)
@@ -396,15 +460,15 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
     };
 
     if (two) { CU(cudaEventRecord(c->ev_main, S)); CU(cudaStreamWaitEvent(T, c->ev_main, 0)); }
-    int b = 0, sbase = 0;
-    int gn = (nblk - b < gsz) ? nblk - b : gsz;
+    int b = kb0, sbase = 0;
+    int gn = (kb1 - b < gsz) ? kb1 - b : gsz;
     c->cur = T;
     if ((rc = pivot_group(b, gn, sbase)) != FW_OK) { c->cur = nullptr; return rc; }
     if (two) CU(cudaEventRecord(c->ev_side, T));
-    while (b < nblk && nblk > 1) {
+    while (b < kb1 && nblk > 1) {
         const int b0 = b * FW_B, u0 = b0 / 64;
         const int bn = b + gn;                                          // first block of the next group
-        const int gnn = (nblk - bn < gsz) ? nblk - bn : gsz;            // its size (0: none)
+        const int gnn = (kb1 - bn < gsz) ? kb1 - bn : gsz;              // its size (0: none)
         const int uL = u0 + 2 * (gn - 1);                               // units of the LAST block of this group
         c->cur = S;
         if (two) CU(cudaStreamWaitEvent(S, c->ev_side, 0));             // panels of this group are ready
@@ -528,17 +592,19 @@ int solve_device_locked(fw_ctx *c, int n, long long ld, double *rate, int32_t *n
     return FW_OK;
 }
 
-fw_ctx *g_default = nullptr;
+std::atomic<fw_ctx *> g_default{nullptr};
 std::mutex g_default_mu;
 
 int get_ctx(fw_ctx *in, fw_ctx **out) {
     if (in) { *out = in; return FW_OK; }
     std::lock_guard<std::mutex> lk(g_default_mu);
-    if (!g_default) {
-        int rc = fw_ctx_create(0, &g_default);
+    if (!g_default.load()) {
+        fw_ctx *d = nullptr;
+        int rc = fw_ctx_create(0, &d);
         if (rc != FW_OK) return rc;
+        g_default.store(d);
     }
-    *out = g_default;
+    *out = g_default.load();
     return FW_OK;
 }
 
@@ -553,6 +619,18 @@ extern "C" {
 
 const char *fw_version(void) { return "fwgpu 0.1 (sm_100a, exact-order blocked max-times Floyd-Warshall)"; }
 const char *fw_last_error(void) { return g_err.c_str(); }
+
+// Text of the last failure of a call made on `ctx` (NULL: the process-wide default context), valid until the
+// next failing call on that context.  Unlike fw_last_error it does not depend on the calling OS thread.
+const char *fw_ctx_last_error(fw_ctx *c) {
+    if (!c) {
+        c = g_default.load();
+        if (!c) return g_err.c_str();   // the default context could not even be created: this thread's text
+    }
+    std::lock_guard<std::mutex> lk(c->err_mu);
+    c->err_ret = c->err;                 // stable copy handed to the caller
+    return c->err_ret.c_str();
+}
 
 int fw_device_count(void) {
     int n = 0;
@@ -597,6 +675,7 @@ void fw_ctx_destroy(fw_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->edge_state) { fw_state_destroy(c->edge_state); c->edge_state = nullptr; }
+    if (c->pscratch) { c->pscratch->release(); delete c->pscratch; c->pscratch = nullptr; }
     for (int i = 0; i < 16; ++i) { c->Cp[i].release(); c->Rw[i].release(); c->NCp[i].release(); }
     c->w_rate.release(); c->w_next.release(); c->w_mid.release(); c->w_csT.release(); c->w_rs.release();
     c->s_rate.release(); c->s_next.release(); c->s_mid.release(); c->s_csT.release(); c->s_rs.release();
@@ -610,8 +689,9 @@ void fw_ctx_destroy(fw_ctx *c) {
 }
 
 int fw_ctx_set_stream(fw_ctx *c, void *cuda_stream, int external) {
+    ErrScope es0__(c);
     if (!c) return fail(FW_ERR_INVALID, "fw_ctx_set_stream: null context");
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     c->stream = external ? (cudaStream_t)cuda_stream : c->own_stream;
     return FW_OK;
 }
@@ -619,15 +699,17 @@ int fw_ctx_set_stream(fw_ctx *c, void *cuda_stream, int external) {
 int64_t fw_ctx_last_launches(const fw_ctx *c) { return c ? c->launches : 0; }
 
 int fw_ctx_set_profiling(fw_ctx *c, int on) {
+    ErrScope es0__(c);
     if (!c) return fail(FW_ERR_INVALID, "fw_ctx_set_profiling: null context");
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     c->profiling = (on != 0);
     return FW_OK;
 }
 
 int64_t fw_ctx_phase_spans(fw_ctx *c, int phase, double *ms, int64_t cap) {
+    ErrScope es0__(c);
     if (!c || phase < 0 || phase > 3 || (!ms && cap > 0)) return fail(FW_ERR_INVALID, "fw_ctx_phase_spans: bad argument");
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     if (cudaSetDevice(c->device) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
         return fail(FW_ERR_CUDA, "fw_ctx_phase_spans: stream synchronize failed");
     int64_t n = 0;
@@ -644,8 +726,9 @@ int64_t fw_ctx_phase_spans(fw_ctx *c, int phase, double *ms, int64_t cap) {
 }
 
 int fw_ctx_phase_ms(fw_ctx *c, double ms[4], int64_t count[4]) {
+    ErrScope es0__(c);
     if (!c || !ms || !count) return fail(FW_ERR_INVALID, "fw_ctx_phase_ms: bad argument");
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < 4; ++i) { ms[i] = 0.0; count[i] = 0; }
@@ -668,27 +751,65 @@ int fw_ctx_synchronize(fw_ctx *c) {
 
 int fw_solve_device(fw_ctx *c, int32_t n, int64_t ld, double *d_rate, int32_t *d_next, int32_t *d_mid,
                     int32_t *d_csT, int32_t *d_rs) {
+    ErrScope es0__(c);
     if (n < 0) return fail(FW_ERR_INVALID, "fw_solve_device: n < 0");
     if (n == 0) return FW_OK;
     if (!d_rate || !d_next || ld < n) return fail(FW_ERR_INVALID, "fw_solve_device: bad argument");
     if (!paths_args_ok(d_mid, d_csT, d_rs)) return fail(FW_ERR_INVALID, "mid/csT/rs: pass all three or none");
     int rc = get_ctx(c, &c);
     if (rc != FW_OK) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     CU(cudaSetDevice(c->device));
     c->launches = 0;
     recycle_spans(c);
     return solve_device_locked(c, n, ld, d_rate, d_next, d_mid, d_csT, d_rs, true);
 }
 
+int fw_solve_device_range(fw_ctx *c, int32_t n, int64_t ld, double *d_rate, int32_t *d_next, int32_t *d_mid,
+                          int32_t *d_csT, int32_t *d_rs, int32_t kb0, int32_t kb1) {
+    if (n <= 0 || n % FW_B) return fail(FW_ERR_INVALID, "fw_solve_device_range: n must be a positive multiple of 128");
+    if (!d_rate || !d_next || ld < n || ld % 4 || ((uintptr_t)d_rate & 15) || ((uintptr_t)d_next & 15))
+        return fail(FW_ERR_INVALID, "fw_solve_device_range: bad argument (ld % 4 == 0, 16-byte aligned)");
+    if (!paths_args_ok(d_mid, d_csT, d_rs)) return fail(FW_ERR_INVALID, "mid/csT/rs: pass all three or none");
+    if (kb0 < 0 || kb1 < kb0 || kb1 > n / FW_B) return fail(FW_ERR_INVALID, "fw_solve_device_range: bad k-block range");
+    int rc = get_ctx(c, &c);
+    if (rc != FW_OK) return rc;
+    FW_ENTER(c);
+    CU(cudaSetDevice(c->device));
+    c->launches = 0;
+    recycle_spans(c);
+    c->cur = nullptr;
+    if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
+    if (kb0 == 0) {
+        if ((rc = validate_device(c, d_rate, d_next, ld, 0, 1, n)) != FW_OK) return rc;
+        if (d_mid) {
+            if ((rc = fill_minus1_2d(c, d_mid, ld, n, n)) != FW_OK) return rc;
+            if ((rc = fill_minus1_2d(c, d_csT, ld, n, n)) != FW_OK) return rc;
+            if ((rc = fill_minus1_2d(c, d_rs, ld, n, n)) != FW_OK) return rc;
+        }
+    }
+    if (kb0 == kb1) return FW_OK;
+    if (n == FW_B) return solve_tiles(c, 1, n, ld, 0, d_rate, d_next, d_mid, d_csT, d_rs);
+    return solve_blocked(c, n, ld, d_rate, d_next, d_mid, d_csT, d_rs, kb0, kb1);
+}
+
+int fw_ctx_set_row_snapshot_sink(fw_ctx *c, double *d_sink, int64_t ld) {
+    if (!c || (d_sink && ld <= 0)) return fail(FW_ERR_INVALID, "fw_ctx_set_row_snapshot_sink: bad argument");
+    FW_ENTER(c);
+    c->snap_sink = d_sink;
+    c->snap_ld = ld;
+    return FW_OK;
+}
+
 int fw_solve(fw_ctx *c, int32_t n, double *rate, int32_t *next, int32_t *mid, int32_t *csT, int32_t *rs) {
+    ErrScope es0__(c);
     if (n < 0) return fail(FW_ERR_INVALID, "fw_solve: n < 0");
     if (n == 0) return FW_OK;  // floydWarshall M.empty == V.empty
     if (!rate || !next) return fail(FW_ERR_INVALID, "fw_solve: null buffer");
     if (!paths_args_ok(mid, csT, rs)) return fail(FW_ERR_INVALID, "mid/csT/rs: pass all three or none");
     int rc = get_ctx(c, &c);
     if (rc != FW_OK) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     CU(cudaSetDevice(c->device));
     c->launches = 0;
     recycle_spans(c);
@@ -744,13 +865,14 @@ int fw_solve(fw_ctx *c, int32_t n, double *rate, int32_t *next, int32_t *mid, in
 
 int fw_solve_batched_device(fw_ctx *c, int32_t batch, int32_t n, double *d_rate, int32_t *d_next,
                             int32_t *d_mid, int32_t *d_csT, int32_t *d_rs) {
+    ErrScope es0__(c);
     if (n < 0 || batch < 0) return fail(FW_ERR_INVALID, "fw_solve_batched_device: negative size");
     if (n == 0 || batch == 0) return FW_OK;
     if (!d_rate || !d_next) return fail(FW_ERR_INVALID, "fw_solve_batched_device: null buffer");
     if (!paths_args_ok(d_mid, d_csT, d_rs)) return fail(FW_ERR_INVALID, "mid/csT/rs: pass all three or none");
     int rc = get_ctx(c, &c);
     if (rc != FW_OK) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     CU(cudaSetDevice(c->device));
     c->launches = 0;
     recycle_spans(c);
@@ -776,6 +898,7 @@ int fw_solve_batched_device(fw_ctx *c, int32_t batch, int32_t n, double *d_rate,
 
 int fw_solve_batched(fw_ctx *c, int32_t batch, int32_t n, double *rate, int32_t *next, int32_t *mid,
                      int32_t *csT, int32_t *rs) {
+    ErrScope es0__(c);
     if (n < 0 || batch < 0) return fail(FW_ERR_INVALID, "fw_solve_batched: negative size");
     if (n == 0 || batch == 0) return FW_OK;
     if (!rate || !next) return fail(FW_ERR_INVALID, "fw_solve_batched: null buffer");
@@ -784,8 +907,8 @@ int fw_solve_batched(fw_ctx *c, int32_t batch, int32_t n, double *rate, int32_t 
     if (rc != FW_OK) return rc;
     const size_t tot = (size_t)batch * n * n;
     const bool paths = (mid != nullptr);
+    FW_ENTER(c);   // held across upload, solve and download (the staging buffers belong to the context)
     {
-        std::lock_guard<std::mutex> lk(c->mu);
         CU(cudaSetDevice(c->device));
         if ((rc = c->s_rate.ensure(tot)) != FW_OK) return rc;
         if ((rc = c->s_next.ensure(tot)) != FW_OK) return rc;
@@ -800,7 +923,6 @@ int fw_solve_batched(fw_ctx *c, int32_t batch, int32_t n, double *rate, int32_t 
     rc = fw_solve_batched_device(c, batch, n, c->s_rate.p, c->s_next.p, paths ? c->s_mid.p : nullptr,
                                  paths ? c->s_csT.p : nullptr, paths ? c->s_rs.p : nullptr);
     if (rc != FW_OK) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
     CU(cudaMemcpyAsync(rate, c->s_rate.p, tot * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(next, c->s_next.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
     if (paths) {
@@ -813,9 +935,133 @@ int fw_solve_batched(fw_ctx *c, int32_t batch, int32_t n, double *rate, int32_t 
 }
 
 /* ---- exact `_path` expansion (Algorithms.hs:55) --------------------------- */
+}  // extern "C"
+
+namespace {
+
+fw_path_scratch *path_scratch(fw_ctx *c) {
+    if (!c->pscratch) c->pscratch = new (std::nothrow) fw_path_scratch();
+    return c->pscratch;
+}
+
+fw::PathTables one_shard_tables(int n, long long ld, const int32_t *init_next, const int32_t *mid, const int32_t *csT,
+                                const int32_t *rs) {
+    fw::PathTables t;
+    for (int i = 0; i < fw::PATH_MAXSHARD; ++i) { t.init_next[i] = init_next; t.mid[i] = mid; t.csT[i] = csT; t.rs[i] = rs; }
+    t.ld = ld; t.n = n; t.rows_per = n > 0 ? n : 1;
+    return t;
+}
+
+constexpr long long PATH_MAX_LEN = 1LL << 24;   // hard per-path bound (arbitrage cycles make paths grow exponentially)
+
+// Paths of nq (src, dst) pairs against device tables `t` (possibly row-sharded, peers mapped).  Context lock held.
+int paths_locked(fw_ctx *c, const fw::PathTables &t, int32_t nq, const int32_t *queries, int64_t *offsets,
+                 int32_t *verts, int64_t cap) {
+    fw_path_scratch *ps = path_scratch(c);
+    if (!ps) return fail(FW_ERR_NOMEM, "out of host memory");
+    int rc;
+    if ((rc = ps->q.ensure(2 * (size_t)nq)) != FW_OK || (rc = ps->len.ensure(nq)) != FW_OK ||
+        (rc = ps->off.ensure((size_t)nq + 1)) != FW_OK || (rc = ps->h_len.ensure((size_t)nq + 1)) != FW_OK)
+        return rc;
+    fw::PathArgs a;
+    a.t = t; a.nq = nq; a.queries = ps->q.p; a.lengths = ps->len.p; a.offsets = ps->off.p; a.verts = nullptr;
+    a.max_len = PATH_MAX_LEN; a.gstack = nullptr; a.gcap = 0; a.flag = c->d_flag;
+    CU(cudaMemcpyAsync(ps->q.p, queries, sizeof(int32_t) * 2 * (size_t)nq, cudaMemcpyHostToDevice, c->stream));
+    // pass 0 (lengths); a second attempt with a global overflow stack if some walk went deeper than the local one
+    int q_chunk = nq;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        for (int q0 = 0; q0 < nq; q0 += q_chunk) {
+            const int qn = (nq - q0 < q_chunk) ? nq - q0 : q_chunk;
+            fw::PathArgs b = a;
+            b.nq = qn; b.queries = a.queries + 2 * (size_t)q0; b.lengths = a.lengths + q0;
+            if (q0 == 0) CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
+            fw::fw_paths_kernel<0><<<(qn + 63) / 64, 64, 0, c->stream>>>(b);
+            c->launches++;
+        }
+        CU(cudaMemcpyAsync(ps->h_len.p, ps->len.p, sizeof(long long) * (size_t)nq, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (!(*c->h_flag & 1) || attempt == 1) break;
+        // deep recursion (arbitrage): n + 2 overflow slots per walk always suffice; bound the scratch to ~256 MB
+        a.gcap = (long long)t.n + 2;
+        const long long per = a.gcap * 8;
+        q_chunk = (int)std::max<long long>(1, std::min<long long>(nq, (256LL << 20) / per));
+        if ((rc = ps->gstack.ensure((size_t)q_chunk * (size_t)a.gcap)) != FW_OK) return rc;
+        a.gstack = ps->gstack.p;
+    }
+    if (*c->h_flag & 4) return fail(FW_ERR_INVALID, "fw_paths: query vertex out of range");
+    if (*c->h_flag & 1) return fail(FW_ERR_CAP, "fw_paths: path recursion deeper than the device stack");
+    long long *h_off = ps->h_len.p;      // lengths -> exclusive prefix sums, in place (back to front is not needed: use a carry)
+    long long run = 0;
+    offsets[0] = 0;
+    for (int i = 0; i < nq; ++i) { const long long l = h_off[i]; h_off[i] = run; run += l; offsets[i + 1] = run; }
+    h_off[nq] = run;
+    if (*c->h_flag & 2) return fail(FW_ERR_CAP, "fw_paths: a path is longer than 2^24 hops");
+    if (run > cap) return fail(FW_ERR_CAP, "fw_paths: output capacity too small (offsets[nq] holds the size needed)");
+    if (run > 0) {
+        if (!verts) return fail(FW_ERR_INVALID, "fw_paths: verts is null");
+        if ((rc = ps->verts.ensure((size_t)run)) != FW_OK) return rc;
+        a.verts = ps->verts.p;
+        CU(cudaMemcpyAsync(ps->off.p, h_off, sizeof(long long) * ((size_t)nq + 1), cudaMemcpyHostToDevice, c->stream));
+        for (int q0 = 0; q0 < nq; q0 += q_chunk) {
+            const int qn = (nq - q0 < q_chunk) ? nq - q0 : q_chunk;
+            fw::PathArgs b = a;
+            b.nq = qn; b.queries = a.queries + 2 * (size_t)q0; b.offsets = a.offsets + q0;
+            fw::fw_paths_kernel<1><<<(qn + 63) / 64, 64, 0, c->stream>>>(b);
+            c->launches++;
+        }
+        CU(cudaMemcpyAsync(verts, ps->verts.p, sizeof(int32_t) * (size_t)run, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return FW_OK;
+}
+
+// optimum for one pair in one launch (fw_optimum_kernel) -> mapped pinned record.  Context lock held.
+int optimum_locked(fw_ctx *c, const fw::PathTables &t, const double *const *rate_shards, long long rate_ld, int32_t src,
+                   int32_t dst, double *rate, int32_t *path, int32_t cap, int32_t *path_len) {
+    fw_path_scratch *ps = path_scratch(c);
+    if (!ps) return fail(FW_ERR_NOMEM, "out of host memory");
+    int rc;
+    const int kcap = cap < 4096 ? cap : 4096;        // vertices returned through the mapped record; longer paths take fw_paths
+    if ((rc = ps->h_opt.ensure(16 + 4 * (size_t)4096)) != FW_OK) return rc;
+    if ((rc = ps->gstack.ensure((size_t)t.n + 2)) != FW_OK) return rc;
+    fw::OptimumArgs a;
+    a.t = t;
+    for (int i = 0; i < fw::PATH_MAXSHARD; ++i) a.rate[i] = rate_shards[i];
+    a.rate_ld = rate_ld; a.src = src; a.dst = dst; a.cap = kcap; a.max_len = PATH_MAX_LEN;
+    a.gstack = ps->gstack.p; a.gcap = (long long)t.n + 2;
+    void *dview = nullptr;
+    CU(cudaHostGetDevicePointer(&dview, ps->h_opt.p, 0));
+    a.out = static_cast<unsigned char *>(dview);
+    fw::fw_optimum_kernel<<<1, 32, 0, c->stream>>>(a);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    double r; long long len;
+    memcpy(&r, ps->h_opt.p, 8);
+    memcpy(&len, ps->h_opt.p + 8, 8);
+    *rate = r;
+    if (len == -1) return fail(FW_ERR_CAP, "fw_state_optimum: path recursion deeper than the device stack");
+    if (len == -2) { *path_len = 0; return fail(FW_ERR_CAP, "fw_state_optimum: the path is longer than 2^24 hops"); }
+    *path_len = (int32_t)len;
+    if (len > cap) return fail(FW_ERR_CAP, "fw_state_optimum: path capacity too small (*path_len holds the size needed)");
+    if (len <= kcap) {
+        if (len > 0) memcpy(path, ps->h_opt.p + 16, 4 * (size_t)len);
+        return FW_OK;
+    }
+    const int32_t q[2] = {src, dst};
+    int64_t off[2] = {0, 0};
+    return paths_locked(c, t, 1, q, off, path, cap);
+}
+
+}  // namespace
+
+extern "C" {
+
 int fw_paths_device(fw_ctx *c, int32_t n, int64_t ld, const int32_t *d_init_next, const int32_t *d_mid,
                     const int32_t *d_csT, const int32_t *d_rs, int32_t nq, const int32_t *queries,
                     int64_t *offsets, int32_t *verts, int64_t cap) {
+    ErrScope es0__(c);
     if (n < 0 || nq < 0 || !offsets) return fail(FW_ERR_INVALID, "fw_paths: bad argument");
     offsets[0] = 0;
     if (nq == 0 || n == 0) { for (int i = 0; i < nq; ++i) offsets[i + 1] = 0; return FW_OK; }
@@ -823,76 +1069,75 @@ int fw_paths_device(fw_ctx *c, int32_t n, int64_t ld, const int32_t *d_init_next
         return fail(FW_ERR_INVALID, "fw_paths: null table");
     int rc = get_ctx(c, &c);
     if (rc != FW_OK) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     CU(cudaSetDevice(c->device));
-    int32_t *d_q = nullptr; long long *d_len = nullptr, *d_off = nullptr; int32_t *d_verts = nullptr;
-    auto cleanup = [&]() { cudaFree(d_q); cudaFree(d_len); cudaFree(d_off); cudaFree(d_verts); };
-    std::vector<long long> h_len(nq), h_off((size_t)nq + 1);
-    cudaError_t e;
-    if ((e = cudaMalloc(&d_q, sizeof(int32_t) * 2 * (size_t)nq)) != cudaSuccess ||
-        (e = cudaMalloc(&d_len, sizeof(long long) * (size_t)nq)) != cudaSuccess ||
-        (e = cudaMalloc(&d_off, sizeof(long long) * ((size_t)nq + 1))) != cudaSuccess) {
-        cleanup(); return cuda_fail(e, "cudaMalloc");
+    return paths_locked(c, one_shard_tables(n, ld, d_init_next, d_mid, d_csT, d_rs), nq, queries, offsets, verts, cap);
+}
+
+/* The four n x n tables of one optimised matrix kept on the device, so that `_path` thunks of the same
+ * Matrix RateEntry are expanded without re-uploading them (one upload per matrix, not per entry). */
+struct fw_tables {
+    fw_ctx *ctx = nullptr;
+    int n = 0;
+    DevBuf<int32_t> t[4];
+};
+
+int fw_tables_create(fw_ctx *c, int32_t n, const int32_t *init_next, const int32_t *mid, const int32_t *csT,
+                     const int32_t *rs, fw_tables **out) {
+    ErrScope es0__(c);
+    if (!out || n < 0) return fail(FW_ERR_INVALID, "fw_tables_create: bad argument");
+    *out = nullptr;
+    if (n > 0 && (!init_next || !mid || !csT || !rs)) return fail(FW_ERR_INVALID, "fw_tables_create: null table");
+    int rc = get_ctx(c, &c);
+    if (rc != FW_OK) return rc;
+    FW_ENTER(c);
+    CU(cudaSetDevice(c->device));
+    fw_tables *t = new (std::nothrow) fw_tables();
+    if (!t) return fail(FW_ERR_NOMEM, "out of host memory");
+    t->ctx = c; t->n = n;
+    const size_t tot = (size_t)n * n;
+    const int32_t *h[4] = {init_next, mid, csT, rs};
+    for (int i = 0; i < 4 && tot > 0; ++i) {
+        rc = t->t[i].ensure(tot);
+        cudaError_t e = cudaSuccess;
+        if (rc == FW_OK) e = cudaMemcpyAsync(t->t[i].p, h[i], tot * 4, cudaMemcpyHostToDevice, c->stream);
+        if (rc == FW_OK && e != cudaSuccess) rc = cuda_fail(e, "fw_tables_create upload");
+        if (rc != FW_OK) { for (int j = 0; j < 4; ++j) t->t[j].release(); delete t; return rc; }
     }
-    fw::PathArgs a;
-    a.init_next = d_init_next; a.mid = d_mid; a.csT = d_csT; a.rs = d_rs; a.ld = ld; a.n = n; a.nq = nq;
-    a.queries = d_q; a.lengths = d_len; a.offsets = d_off; a.verts = nullptr;
-    a.max_len = 1LL << 24;   // hard per-path bound (arbitrage cycles make paths grow exponentially)
-    a.flag = c->d_flag;
-    const int grid = (nq + 63) / 64;
-    if ((e = cudaMemcpyAsync(d_q, queries, sizeof(int32_t) * 2 * (size_t)nq, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
-        (e = cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream)) != cudaSuccess) { cleanup(); return cuda_fail(e, "copy"); }
-    fw::fw_paths_kernel<0><<<grid, 64, 0, c->stream>>>(a);
-    c->launches++;
-    if ((e = cudaMemcpyAsync(h_len.data(), d_len, sizeof(long long) * (size_t)nq, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
-        (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { cleanup(); return cuda_fail(e, "fw_paths pass 0"); }
-    if (*c->h_flag & 4) { cleanup(); return fail(FW_ERR_INVALID, "fw_paths: query vertex out of range"); }
-    if (*c->h_flag & 1) { cleanup(); return fail(FW_ERR_CAP, "fw_paths: path recursion deeper than the device stack"); }
-    h_off[0] = 0;
-    for (int i = 0; i < nq; ++i) h_off[i + 1] = h_off[i] + h_len[i];
-    for (int i = 0; i <= nq; ++i) offsets[i] = h_off[i];
-    if (*c->h_flag & 2) { cleanup(); return fail(FW_ERR_CAP, "fw_paths: a path is longer than 2^24 hops"); }
-    if (h_off[nq] > cap) {
-        cleanup();
-        return fail(FW_ERR_CAP, "fw_paths: output capacity too small (offsets[nq] holds the size needed)");
-    }
-    if (h_off[nq] > 0) {
-        if (!verts) { cleanup(); return fail(FW_ERR_INVALID, "fw_paths: verts is null"); }
-        if ((e = cudaMalloc(&d_verts, sizeof(int32_t) * (size_t)h_off[nq])) != cudaSuccess) { cleanup(); return cuda_fail(e, "cudaMalloc"); }
-        a.verts = d_verts;
-        if ((e = cudaMemcpyAsync(d_off, h_off.data(), sizeof(long long) * ((size_t)nq + 1), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) { cleanup(); return cuda_fail(e, "copy"); }
-        fw::fw_paths_kernel<1><<<grid, 64, 0, c->stream>>>(a);
-        c->launches++;
-        if ((e = cudaMemcpyAsync(verts, d_verts, sizeof(int32_t) * (size_t)h_off[nq], cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
-            (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) { cleanup(); return cuda_fail(e, "fw_paths pass 1"); }
-    }
-    cleanup();
+    cudaError_t e = cudaStreamSynchronize(c->stream);   // the host tables may be freed by the caller after this returns
+    if (e != cudaSuccess) { for (int j = 0; j < 4; ++j) t->t[j].release(); delete t; return cuda_fail(e, "fw_tables_create"); }
+    *out = t;
     return FW_OK;
+}
+
+void fw_tables_destroy(fw_tables *t) {
+    if (!t) return;
+    FW_ENTER(t->ctx);
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    for (int j = 0; j < 4; ++j) t->t[j].release();
+    delete t;
+}
+
+int fw_tables_paths(fw_tables *t, int32_t nq, const int32_t *queries, int64_t *offsets, int32_t *verts, int64_t cap) {
+    if (!t || nq < 0 || !offsets) return fail(FW_ERR_INVALID, "fw_tables_paths: bad argument");
+    return fw_paths_device(t->ctx, t->n, t->n, t->t[0].p, t->t[1].p, t->t[2].p, t->t[3].p, nq, queries, offsets, verts, cap);
 }
 
 int fw_paths(fw_ctx *c, int32_t n, const int32_t *init_next, const int32_t *mid, const int32_t *csT,
              const int32_t *rs, int32_t nq, const int32_t *queries, int64_t *offsets, int32_t *verts,
              int64_t cap) {
+    ErrScope es0__(c);
     if (n < 0 || nq < 0 || !offsets) return fail(FW_ERR_INVALID, "fw_paths: bad argument");
     if (n == 0 || nq == 0) return fw_paths_device(c, n, n, nullptr, nullptr, nullptr, nullptr, nq, queries, offsets, verts, cap);
     if (!init_next || !mid || !csT || !rs) return fail(FW_ERR_INVALID, "fw_paths: null table");
     int rc = get_ctx(c, &c);
     if (rc != FW_OK) return rc;
-    const size_t tot = (size_t)n * n;
-    int32_t *d[4] = {nullptr, nullptr, nullptr, nullptr};
-    const int32_t *h[4] = {init_next, mid, csT, rs};
-    {
-        std::lock_guard<std::mutex> lk(c->mu);
-        CU(cudaSetDevice(c->device));
-        for (int i = 0; i < 4; ++i) {
-            cudaError_t e = cudaMalloc(&d[i], tot * 4);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(d[i], h[i], tot * 4, cudaMemcpyHostToDevice, c->stream);
-            if (e != cudaSuccess) { for (int j = 0; j < 4; ++j) cudaFree(d[j]); return cuda_fail(e, "fw_paths upload"); }
-        }
-    }
-    rc = fw_paths_device(c, n, n, d[0], d[1], d[2], d[3], nq, queries, offsets, verts, cap);
-    for (int j = 0; j < 4; ++j) cudaFree(d[j]);
+    FW_ENTER(c);      // held across upload and expansion
+    fw_tables *t = nullptr;
+    if ((rc = fw_tables_create(c, n, init_next, mid, csT, rs, &t)) != FW_OK) return rc;
+    rc = fw_tables_paths(t, nq, queries, offsets, verts, cap);
+    fw_tables_destroy(t);
     return rc;
 }
 
@@ -923,13 +1168,14 @@ static int build_matrix_locked(fw_ctx *c, int n, long long ld, const int32_t *d_
 
 int fw_build_matrix_device(fw_ctx *c, int32_t n, int64_t ld, const int32_t *ccy, int32_t m, const int32_t *src,
                            const int32_t *dst, const double *val, double *d_rate, int32_t *d_next) {
+    ErrScope es0__(c);
     if (n < 0 || m < 0) return fail(FW_ERR_INVALID, "fw_build_matrix_device: negative size");
     if (n == 0) return FW_OK;
     if (!ccy || !d_rate || !d_next || ld < n || (m > 0 && (!src || !dst || !val)))
         return fail(FW_ERR_INVALID, "fw_build_matrix_device: bad argument");
     int rc = get_ctx(c, &c);
     if (rc != FW_OK) return rc;
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     CU(cudaSetDevice(c->device));
     c->launches = 0;
     DevBuf<int32_t> dccy, dsrc, ddst; DevBuf<double> dval;
@@ -953,6 +1199,7 @@ int fw_build_matrix_device(fw_ctx *c, int32_t n, int64_t ld, const int32_t *ccy,
 }
 
 int fw_state_create(fw_ctx *c, fw_state **out) {
+    ErrScope es0__(c);
     if (!out) return fail(FW_ERR_INVALID, "fw_state_create: null output");
     *out = nullptr;
     int rc = get_ctx(c, &c);
@@ -977,7 +1224,7 @@ int fw_state_sync(fw_state *s, int32_t n, const int32_t *ccy, int32_t m, const i
                   const double *val) {
     if (!s || n < 0 || m < 0) return fail(FW_ERR_INVALID, "fw_state_sync: bad argument");
     fw_ctx *c = s->ctx;
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     CU(cudaSetDevice(c->device));
     c->launches = 0;
     recycle_spans(c);
@@ -1019,28 +1266,23 @@ int fw_state_optimum(fw_state *s, int32_t src, int32_t dst, double *rate, int32_
                      int32_t *path_len) {
     if (!s || !rate || !path_len || cap < 0 || (cap > 0 && !path))
         return fail(FW_ERR_INVALID, "fw_state_optimum: bad argument");
+    fw_ctx *c = s->ctx;
+    FW_ENTER(c);
     if (!s->synced) return fail(FW_ERR_INVALID, "fw_state_optimum: state is not in sync (call fw_state_sync)");
     if (!s->want_paths) return fail(FW_ERR_INVALID, "fw_state_optimum: state was synced without path tables");
     if (src < 0 || dst < 0 || src >= s->n || dst >= s->n) return fail(FW_ERR_INVALID, "fw_state_optimum: vertex index out of range");
-    fw_ctx *c = s->ctx;
-    {
-        std::lock_guard<std::mutex> lk(c->mu);
-        CU(cudaSetDevice(c->device));
-        CU(cudaMemcpyAsync(rate, s->rate.p + (size_t)src * s->n + dst, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-    }
-    const int32_t q[2] = {src, dst};
-    int64_t off[2] = {0, 0};
-    int rc = fw_paths_device(c, s->n, s->n, s->init_next.p, s->mid.p, s->csT.p, s->rs.p, 1, q, off, path, cap);
-    *path_len = (int32_t)off[1];
-    return rc;
+    CU(cudaSetDevice(c->device));
+    const double *rs[fw::PATH_MAXSHARD];
+    for (int i = 0; i < fw::PATH_MAXSHARD; ++i) rs[i] = s->rate.p;
+    return optimum_locked(c, one_shard_tables(s->n, s->n, s->init_next.p, s->mid.p, s->csT.p, s->rs.p), rs, s->n,
+                          src, dst, rate, path, cap, path_len);
 }
 
 int fw_state_download(fw_state *s, double *rate, int32_t *next) {
     if (!s || !s->synced) return fail(FW_ERR_INVALID, "fw_state_download: state is not in sync");
     if (s->n == 0) return FW_OK;
     fw_ctx *c = s->ctx;
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     CU(cudaSetDevice(c->device));
     const size_t tot = (size_t)s->n * s->n;
     if (rate) CU(cudaMemcpyAsync(rate, s->rate.p, tot * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1054,32 +1296,30 @@ int fw_state_download(fw_state *s, double *rate, int32_t *next) {
 int fw_solve_edges(fw_ctx *c, int32_t n, const int32_t *ccy, int32_t m, const int32_t *src, const int32_t *dst,
                    const double *val, double *rate, int32_t *next, int32_t *init_next, int32_t *mid, int32_t *csT,
                    int32_t *rs) {
+    ErrScope es0__(c);
     if (n < 0 || m < 0) return fail(FW_ERR_INVALID, "fw_solve_edges: negative size");
     if (n == 0) return FW_OK;
     if (!rate || !next) return fail(FW_ERR_INVALID, "fw_solve_edges: null output");
     if (!paths_args_ok(mid, csT, rs)) return fail(FW_ERR_INVALID, "mid/csT/rs: pass all three or none");
     int rc = get_ctx(c, &c);
     if (rc != FW_OK) return rc;
+    FW_ENTER(c);   // one lock from the creation of the cached state to the end of the download
     if (!c->edge_state && (rc = fw_state_create(c, &c->edge_state)) != FW_OK) return rc;
     fw_state *st = c->edge_state;
     st->want_paths = (mid != nullptr) || (init_next != nullptr);
     rc = fw_state_sync(st, n, ccy, m, src, dst, val);
-    if (rc == FW_OK) {
-        fw_ctx *cc = st->ctx;
-        std::lock_guard<std::mutex> lk(cc->mu);
-        const size_t tot = (size_t)n * n;
-        cudaError_t e = cudaMemcpyAsync(rate, st->rate.p, tot * 8, cudaMemcpyDeviceToHost, cc->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(next, st->next.p, tot * 4, cudaMemcpyDeviceToHost, cc->stream);
-        if (e == cudaSuccess && init_next) e = cudaMemcpyAsync(init_next, st->init_next.p, tot * 4, cudaMemcpyDeviceToHost, cc->stream);
-        if (e == cudaSuccess && mid) {
-            e = cudaMemcpyAsync(mid, st->mid.p, tot * 4, cudaMemcpyDeviceToHost, cc->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(csT, st->csT.p, tot * 4, cudaMemcpyDeviceToHost, cc->stream);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(rs, st->rs.p, tot * 4, cudaMemcpyDeviceToHost, cc->stream);
-        }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(cc->stream);
-        if (e != cudaSuccess) rc = cuda_fail(e, "fw_solve_edges download");
+    if (rc != FW_OK) return rc;
+    const size_t tot = (size_t)n * n;
+    CU(cudaMemcpyAsync(rate, st->rate.p, tot * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(next, st->next.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (init_next) CU(cudaMemcpyAsync(init_next, st->init_next.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (mid) {
+        CU(cudaMemcpyAsync(mid, st->mid.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(csT, st->csT.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(rs, st->rs.p, tot * 4, cudaMemcpyDeviceToHost, c->stream));
     }
-    return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return FW_OK;
 }
 
 /* ---- row-sharded building blocks (multi-GPU) ------------------------------- */
@@ -1094,19 +1334,21 @@ static int shard_args_ok(int32_t n, int32_t row0, int32_t rows, int64_t ld, cons
 
 int fw_shard_validate(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, const double *d_rate,
                       const int32_t *d_next) {
+    ErrScope es0__(c);
     if (!c || n <= 0 || rows <= 0 || !d_rate || !d_next || ld < n)
         return fail(FW_ERR_INVALID, "fw_shard_validate: bad argument");
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     CU(cudaSetDevice(c->device));
     return validate_device(c, d_rate, d_next, ld, 0, 1, n, rows, row0);
 }
 
 int fw_shard_pivot(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
                    int32_t *d_next, int32_t b0, double *d_Rw) {
+    ErrScope es0__(c);
     if (!c || !shard_args_ok(n, row0, rows, ld, d_rate, d_next, b0, d_Rw))
         return fail(FW_ERR_INVALID, "fw_shard_pivot: bad argument (sizes must be multiples of 128, 16-byte aligned)");
     if (b0 < row0 || b0 >= row0 + rows) return fail(FW_ERR_INVALID, "fw_shard_pivot: this shard does not own k-block b0");
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     CU(cudaSetDevice(c->device));
     c->cur = nullptr;
     int rc;
@@ -1141,11 +1383,12 @@ int fw_shard_pivot(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld,
  * mode 2: every local row outside the k-block and outside the 128 rows starting at lr0. */
 int fw_shard_update_ex(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
                        int32_t *d_next, int32_t b0, const double *d_Rw, int32_t mode, int32_t lr0) {
+    ErrScope es0__(c);
     if (!c || !shard_args_ok(n, row0, rows, ld, d_rate, d_next, b0, d_Rw))
         return fail(FW_ERR_INVALID, "fw_shard_update: bad argument (sizes must be multiples of 128, 16-byte aligned)");
     if (mode < 0 || mode > 2 || (mode != 0 && (lr0 < 0 || lr0 % FW_B || lr0 + FW_B > rows)))
         return fail(FW_ERR_INVALID, "fw_shard_update_ex: bad mode / row range");
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     CU(cudaSetDevice(c->device));
     c->cur = nullptr;
     int rc;
@@ -1201,6 +1444,7 @@ int fw_shard_update_ex(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t
 int fw_shard_update_group(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
                           int32_t *d_next, int32_t b0, int32_t nb, const double *const *d_Rw, int32_t mode,
                           int32_t lr0, int32_t lrn) {
+    ErrScope es0__(c);
     if (!c || !d_Rw || nb < 1 || nb > fw::BULK_MAXNB || !shard_args_ok(n, row0, rows, ld, d_rate, d_next, b0, d_Rw[0]))
         return fail(FW_ERR_INVALID, "fw_shard_update_group: bad argument (sizes must be multiples of 128, 16-byte aligned)");
     for (int i = 0; i < nb; ++i)
@@ -1214,7 +1458,7 @@ int fw_shard_update_group(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int6
     if (g0 < 0) g0 = 0;
     if (g1 > rows) g1 = rows;
     const int gn = g1 > g0 ? g1 - g0 : 0;
-    std::lock_guard<std::mutex> lk(c->mu);
+    FW_ENTER(c);
     CU(cudaSetDevice(c->device));
     c->cur = nullptr;
     int rc;
@@ -1283,12 +1527,14 @@ int fw_shard_update_group(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int6
 int fw_shard_update_pair(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
                          int32_t *d_next, int32_t b0, const double *d_Rw0, const double *d_Rw1, int32_t mode,
                          int32_t lr0, int32_t lrn) {
+    ErrScope es0__(c);
     const double *rw[2] = {d_Rw0, d_Rw1};
     return fw_shard_update_group(c, n, row0, rows, ld, d_rate, d_next, b0, 2, rw, mode, lr0, lrn);
 }
 
 int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
                     int32_t *d_next, int32_t b0, const double *d_Rw) {
+    ErrScope es0__(c);
     return fw_shard_update_ex(c, n, row0, rows, ld, d_rate, d_next, b0, d_Rw, 0, 0);
 }
 

@@ -65,8 +65,17 @@ class _Row(Sequence):
             raise IndexError(j)
         return self._m.entry(self._i, j)
 
+    def materialize(self) -> List["RateEntry"]:
+        n = len(self)
+        ps = self._m.index_paths([(self._i, j) for j in range(n)])        # one device call for the whole row
+        return [RateEntry(float(self._m.rate[self._i, j]), self._m.vertices[self._i],
+                          [self._m.vertices[k] for k in ps[j]]) for j in range(n)]
+
     def __eq__(self, other):
-        return len(self) == len(other) and all(a == b for a, b in zip(self, other))
+        if len(self) != len(other):
+            return False
+        theirs = other.materialize() if isinstance(other, _Row) else other
+        return all(a == b for a, b in zip(self.materialize(), theirs))
 
 
 class RateMatrix(Sequence):
@@ -87,6 +96,7 @@ class RateMatrix(Sequence):
         self.next = nxt if nxt is not None else init_next
         self.mid, self.csT, self.rs = mid, csT, rs
         self._ctx = ctx
+        self._tables = None       # device copy of (init_next, mid, csT, rs): uploaded on first use, once
 
     # -- Sequence protocol: rows of RateEntry
     def __len__(self) -> int:
@@ -105,8 +115,13 @@ class RateMatrix(Sequence):
         return (_Row(self, i) for i in range(self.n))
 
     def __eq__(self, other):
+        """Types.hs:24-29 derives Eq entry by entry; here all n*n paths come from ONE device call per side."""
         try:
-            return len(self) == len(other) and all(a == b for a, b in zip(self, other))
+            if len(self) != len(other):
+                return False
+            mine = self.to_lists()
+            theirs = other.to_lists() if isinstance(other, RateMatrix) else other
+            return all(len(a) == len(b) and all(x == y for x, y in zip(a, b)) for a, b in zip(mine, theirs))
         except TypeError:
             return NotImplemented
 
@@ -115,8 +130,10 @@ class RateMatrix(Sequence):
         """Exact reference paths (index lists) for many (i,j) pairs in one device call."""
         if self.mid is None:
             return [[j] if self.init_next[i, j] >= 0 else [] for i, j in pairs]
-        from . import paths
-        return paths.expand(self.init_next, self.mid, self.csT, self.rs, pairs, ctx=self._ctx)
+        if self._tables is None:
+            from . import paths
+            self._tables = paths.DeviceTables(self.init_next, self.mid, self.csT, self.rs, ctx=self._ctx)
+        return self._tables.expand(pairs)
 
     def entry(self, i: int, j: int) -> RateEntry:
         p = self.index_paths([(i, j)])[0]

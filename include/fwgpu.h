@@ -32,11 +32,15 @@
  * Violations return FW_ERR_DOMAIN and leave the buffers untouched.
  * The diagonal is never read nor written (Algorithms.hs:50,54).
  *
- * Errors: 0 = OK, negative = error; text via fw_last_error() (thread-local).
+ * Errors: 0 = OK, negative = error; text via fw_ctx_last_error(ctx) (kept per
+ * context: safe when the failing call and the query run on different OS
+ * threads, as unbound GHC threads do) or fw_last_error() (per OS thread).
  * No exceptions cross this boundary.  There is no CPU fallback: without a
  * CUDA device every compute entry point returns FW_ERR_CUDA.
  *
- * Threading: a context serialises its own calls; distinct contexts may be
+ * Threading: a context serialises its own calls -- every entry point holds the
+ * context's lock from its first to its last touch of the context's buffers
+ * (composite calls such as fw_solve_edges included); distinct contexts may be
  * used from distinct threads.  Entry points call cudaSetDevice themselves, so
  * they may be called from any OS thread (GHC `safe` foreign calls).
  */
@@ -63,6 +67,8 @@ typedef struct fw_ctx fw_ctx; /* opaque: device id, stream, workspace */
 /* ---- library / device ------------------------------------------------- */
 const char *fw_version(void);
 const char *fw_last_error(void);
+/* Text of the last failure of a call made on ctx (NULL: the default context). */
+const char *fw_ctx_last_error(fw_ctx *ctx);
 int fw_device_count(void);
 
 /* Create a context on `device` (>= 0).  Workspace grows on demand. */
@@ -101,6 +107,20 @@ int fw_solve_device(fw_ctx *ctx, int32_t n, int64_t ld, double *d_rate,
                     int32_t *d_next, int32_t *d_mid, int32_t *d_csT,
                     int32_t *d_rs);
 
+/* Verification entry: only the k-blocks [kb0, kb1) (pivots kb0*128 .. kb1*128-1) of the solve, with the
+ * schedule (k-blocks per fused launch, look-ahead) the FULL solve of this n would use.  After the call the
+ * matrix is the reference loop's state as step kb1*128 begins (Algorithms.hs:44), so a test can compare a
+ * window of the shipped schedule at BASELINE size with a few CPU steps.  n % 128 == 0, ld % 4 == 0,
+ * 16-byte aligned buffers; validation and the mid/csT/rs reset happen only when kb0 == 0. */
+int fw_solve_device_range(fw_ctx *ctx, int32_t n, int64_t ld, double *d_rate,
+                          int32_t *d_next, int32_t *d_mid, int32_t *d_csT,
+                          int32_t *d_rs, int32_t kb0, int32_t kb1);
+/* Verification hook: while set (d_sink != NULL), every solve on ctx also stores row k of the rate matrix AS
+ * STEP k BEGINS into d_sink[k*ld .. k*ld+n) (device memory, n_padded x ld doubles; entry [k][k] is stored as
+ * 0.0).  These are the pivot rows the loop reads (Algorithms.hs:60); with them a CPU oracle can replay any
+ * single row's whole history (oracle/fw_oracle.c: fw_oracle_replay_rows). */
+int fw_ctx_set_row_snapshot_sink(fw_ctx *ctx, double *d_sink, int64_t ld);
+
 /* `batch` independent graphs of the same n, batch-major contiguous
  * (the FSM replay: one full solve per OutSync snapshot,
  * reference src/lib/ProcessRequests.hs:82-84,97-102). */
@@ -117,7 +137,9 @@ int fw_solve_batched_device(fw_ctx *ctx, int32_t batch, int32_t n,
  * init_next[a*n+b] >= 0).  offsets[nq+1] and verts[cap] are host outputs in CSR
  * form.  If the paths need more than `cap` entries the call returns FW_ERR_CAP
  * with offsets filled (offsets[nq] = entries needed) so the caller can re-size.
- * A single path longer than 2^24 hops (arbitrage cycles) is FW_ERR_CAP too.
+ * A single path longer than 2^24 hops (arbitrage cycles) is FW_ERR_CAP too; the
+ * recursion depth is not limited (walks deeper than the 64-slot on-chip stack
+ * continue in a global overflow area, n + 2 slots always suffice).
  * Unreachable pairs yield empty paths.  fw_paths takes HOST tables (n x n),
  * fw_paths_device DEVICE tables with leading dimension ld. */
 int fw_paths(fw_ctx *ctx, int32_t n, const int32_t *init_next, const int32_t *mid,
@@ -127,6 +149,16 @@ int fw_paths_device(fw_ctx *ctx, int32_t n, int64_t ld, const int32_t *d_init_ne
                     const int32_t *d_mid, const int32_t *d_csT, const int32_t *d_rs,
                     int32_t nq, const int32_t *queries, int64_t *offsets, int32_t *verts,
                     int64_t cap);
+
+/* The four tables of ONE optimised matrix uploaded once and kept on the device, so that the lazily
+ * evaluated `_path` fields of a Matrix RateEntry (one thunk per entry) cost one small call each
+ * instead of re-uploading 16 n^2 bytes. */
+typedef struct fw_tables fw_tables;
+int fw_tables_create(fw_ctx *ctx, int32_t n, const int32_t *init_next, const int32_t *mid,
+                     const int32_t *csT, const int32_t *rs, fw_tables **out);
+void fw_tables_destroy(fw_tables *t);
+int fw_tables_paths(fw_tables *t, int32_t nq, const int32_t *queries, int64_t *offsets,
+                    int32_t *verts, int64_t cap);
 
 /* ---- replaces buildMatrix (Algorithms.hs:26-40) on the device ---------------
  * The cache in COO form: n vertices in the reference's sorted order

@@ -213,6 +213,126 @@ int64_t fw_oracle_run_ksteps(int32_t n, double *rate, int32_t *next,
     return updates;
 }
 
+/*
+ * fw_oracle_run_batched -- `batch` independent graphs of order n, batch-major
+ * contiguous; every graph goes through fw_oracle_run_inplace's loop on its own
+ * (OpenMP over the graphs).  The FSM replay (ProcessRequests.hs:82-84: one full
+ * floydWarshall per OutSync snapshot) at BASELINE config C3's full batch.
+ */
+int64_t fw_oracle_run_batched(int32_t batch, int32_t n, double *rate, int32_t *next,
+                              int32_t *mid, int32_t *csT, int32_t *rs, int32_t threads)
+{
+    if (n <= 0 || batch <= 0) return 0;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#else
+    (void)threads;
+#endif
+    const size_t nn = (size_t)n * (size_t)n;
+    int64_t updates = 0;
+#pragma omp parallel for schedule(dynamic, 4) reduction(+ : updates)
+    for (int32_t g = 0; g < batch; ++g) {
+        double *R = rate + g * nn;
+        int32_t *X = next + g * nn;
+        int32_t *M = mid ? mid + g * nn : NULL, *C = csT ? csT + g * nn : NULL, *S = rs ? rs + g * nn : NULL;
+        if (M) for (size_t e = 0; e < nn; ++e) M[e] = -1;
+        for (int32_t k = 0; k < n; ++k) {
+            if (M && C) for (int32_t i = 0; i < n; ++i) C[(size_t)i * n + k] = M[(size_t)i * n + k];
+            if (M && S) for (int32_t j = 0; j < n; ++j) S[(size_t)k * n + j] = M[(size_t)k * n + j];
+            const double *rk = R + (size_t)k * n;
+            const int32_t *nk = X + (size_t)k * n;
+            for (int32_t i = 0; i < n; ++i) {
+                if (i == k) continue;                               /* Algorithms.hs:50 */
+                double *ri = R + (size_t)i * n;
+                int32_t *ni = X + (size_t)i * n;
+                const double ik_rate = ri[k];
+                const int32_t ik_next = ni[k];
+                for (int32_t j = 0; j < n; ++j) {
+                    if (j == i || j == k) continue;                 /* Algorithms.hs:54 */
+                    const double new_rate = ik_rate * rk[j];        /* :61 */
+                    if (ri[j] < new_rate) {                         /* :55 */
+                        ri[j] = new_rate;
+                        ni[j] = (ik_next >= 0) ? ik_next : nk[j];
+                        if (M) M[(size_t)i * n + j] = k;
+                        ++updates;
+                    }
+                }
+            }
+        }
+    }
+    return updates;
+}
+
+/*
+ * fw_oracle_replay_rows -- the reference loop restricted to a SAMPLE of matrix
+ * rows, for sizes where the full O(n^3) loop is out of reach of a test.
+ *
+ * In step k the loop (Algorithms.hs:49-61) touches row i using only row i itself
+ * and row k as it stands when step k begins (row k is not written in step k,
+ * :50).  Given the sequence of those pivot rows  S[k][:] = R_k[k][:]  (recorded
+ * by the implementation under test), the whole history of any single row i
+ * follows from its initial contents:
+ *     for k ascending, k != i:  for j != i, j != k:
+ *         n = row[k] * S[k][j];  if (row[j] < n) { row[j] = n; nx[j] = nx[k]; mid[j] = k }
+ * and at k == i the row must itself equal S[i] -- which ties the recorded
+ * sequence back to the loop.  If every row were replayed this is the full loop
+ * (induction over k); a sample checks the sampled rows' final rates, next-hops
+ * and mids, their csT rows (mid[k] as step k begins) and, at step i, the recorded
+ * pivot row and its rs row, bit for bit.
+ *
+ * rows[r] = sampled row index; row/nx: nrows x n, initial contents in, final out;
+ * mid, csT (nullable): nrows x n out; at_i / mid_at_i (nullable): nrows x n out =
+ * the row and its mids as step i begins.  Returns replacements, -1 - r if row r
+ * met a replacement through an empty path (out of domain: needs row k's next-hops).
+ */
+int64_t fw_oracle_replay_rows(int32_t n, int32_t nrows, const int32_t *rows, const double *S, int64_t ldS,
+                              double *row, int32_t *nx, int32_t *mid, int32_t *csT, double *at_i,
+                              int32_t *mid_at_i, int32_t threads)
+{
+    if (n <= 0 || nrows <= 0) return 0;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#else
+    (void)threads;
+#endif
+    int64_t updates = 0;
+    int32_t bad = -1;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : updates)
+    for (int32_t r = 0; r < nrows; ++r) {
+        const int32_t i = rows[r];
+        double *ri = row + (size_t)r * n;
+        int32_t *ni = nx + (size_t)r * n;
+        int32_t *mi = (int32_t *)malloc((size_t)n * sizeof(int32_t));
+        if (!mi) { bad = r; continue; }
+        for (int32_t j = 0; j < n; ++j) mi[j] = -1;
+        for (int32_t k = 0; k < n; ++k) {
+            if (csT) csT[(size_t)r * n + k] = mi[k];
+            if (k == i) {                                           /* Algorithms.hs:50 */
+                if (at_i) memcpy(at_i + (size_t)r * n, ri, (size_t)n * sizeof(double));
+                if (mid_at_i) memcpy(mid_at_i + (size_t)r * n, mi, (size_t)n * sizeof(int32_t));
+                continue;
+            }
+            const double *sk = S + (size_t)k * (size_t)ldS;
+            const double ik_rate = ri[k];
+            const int32_t ik_next = ni[k];
+            for (int32_t j = 0; j < n; ++j) {
+                if (j == i || j == k) continue;                     /* Algorithms.hs:54 */
+                const double new_rate = ik_rate * sk[j];            /* :61 */
+                if (ri[j] < new_rate) {                             /* :55 */
+                    if (ik_next < 0) bad = r;
+                    ri[j] = new_rate;
+                    ni[j] = ik_next;
+                    mi[j] = k;
+                    ++updates;
+                }
+            }
+        }
+        if (mid) memcpy(mid + (size_t)r * n, mi, (size_t)n * sizeof(int32_t));
+        free(mi);
+    }
+    return bad >= 0 ? -1 - (int64_t)bad : updates;
+}
+
 int32_t fw_oracle_max_threads(void)
 {
 #ifdef _OPENMP

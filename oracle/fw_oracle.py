@@ -194,6 +194,11 @@ def lib():
         L.fw_oracle_run_ksteps.argtypes = [ctypes.c_int32, dp, ip, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_int32]
         L.fw_oracle_max_threads.restype = ctypes.c_int32
+        L.fw_oracle_run_batched.restype = ctypes.c_int64
+        L.fw_oracle_run_batched.argtypes = [ctypes.c_int32, ctypes.c_int32, dp, ip, ip, ip, ip, ctypes.c_int32]
+        L.fw_oracle_replay_rows.restype = ctypes.c_int64
+        L.fw_oracle_replay_rows.argtypes = [ctypes.c_int32, ctypes.c_int32, ip, dp, ctypes.c_int64, dp, ip, ip, ip,
+                                            dp, ip, ctypes.c_int32]
         _lib = L
     return _lib
 
@@ -242,6 +247,52 @@ def run_ksteps(rate: np.ndarray, nxt: np.ndarray, k0: int, k1: int, threads: int
     n = rate.shape[0]
     assert rate.flags.c_contiguous and nxt.flags.c_contiguous
     return int(lib().fw_oracle_run_ksteps(n, _dp(rate), _ip(nxt), k0, k1, threads))
+
+
+def solve_batched(rate: np.ndarray, nxt: np.ndarray, *, paths: bool = False, threads: int = 0) -> DenseResult:
+    """`batch` independent graphs [batch, n, n], each through the reference loop (OpenMP over graphs)."""
+    b, n = rate.shape[0], rate.shape[1]
+    assert rate.shape == (b, n, n) and nxt.shape == (b, n, n)
+    r = np.ascontiguousarray(rate, dtype=np.float64).copy()
+    x = np.ascontiguousarray(nxt, dtype=np.int32).copy()
+    mid = np.empty((b, n, n), dtype=np.int32) if paths else None
+    csT = np.empty((b, n, n), dtype=np.int32) if paths else None
+    rs = np.empty((b, n, n), dtype=np.int32) if paths else None
+    u = lib().fw_oracle_run_batched(b, n, _dp(r), _ip(x), _ip(mid), _ip(csT), _ip(rs), threads)
+    return DenseResult(r, x, mid, csT, rs, int(u))
+
+
+@dataclass
+class RowReplay:
+    rows: np.ndarray       # sampled row indices
+    rate: np.ndarray       # [nrows, n] final rows
+    next: np.ndarray
+    mid: np.ndarray
+    csT: np.ndarray        # [nrows, n] mid[i][k] as step k begins
+    at_i: np.ndarray       # [nrows, n] row i as step i begins (must equal the recorded pivot row S[i])
+    mid_at_i: np.ndarray   # [nrows, n] = rs[i][:]
+    updates: int = 0
+
+
+def replay_rows(rows, S: np.ndarray, init_rate_rows: np.ndarray, init_next_rows: np.ndarray,
+                threads: int = 0) -> RowReplay:
+    """The reference loop on a SAMPLE of rows, given the recorded pivot rows S[k] = row k as step k begins
+    (fw_oracle_replay_rows).  init_*_rows: [nrows, n] initial contents of the sampled rows."""
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    nr, n = len(rows), S.shape[1]
+    assert S.dtype == np.float64 and S.shape[0] >= n and S.strides[1] == 8
+    r = np.ascontiguousarray(init_rate_rows, dtype=np.float64).copy()
+    x = np.ascontiguousarray(init_next_rows, dtype=np.int32).copy()
+    assert r.shape == (nr, n) and x.shape == (nr, n)
+    mid = np.empty((nr, n), dtype=np.int32)
+    csT = np.empty((nr, n), dtype=np.int32)
+    at_i = np.empty((nr, n), dtype=np.float64)
+    mid_at_i = np.empty((nr, n), dtype=np.int32)
+    u = lib().fw_oracle_replay_rows(n, nr, _ip(rows), _dp(S), S.strides[0] // 8, _dp(r), _ip(x), _ip(mid),
+                                    _ip(csT), _dp(at_i), _ip(mid_at_i), threads)
+    if u < 0:
+        raise ValueError(f"replay_rows: row {rows[-1 - u]} replaced an entry through an empty path (out of domain)")
+    return RowReplay(rows, r, x, mid, csT, at_i, mid_at_i, int(u))
 
 
 def max_threads() -> int:
