@@ -26,12 +26,32 @@ SYMBOLS = (
     "fw_version", "fw_last_error", "fw_device_count", "fw_ctx_create", "fw_ctx_destroy",
     "fw_ctx_set_stream", "fw_ctx_last_launches", "fw_solve", "fw_solve_device", "fw_solve_batched",
     "fw_solve_batched_device", "fw_ctx_synchronize", "fw_ctx_set_profiling", "fw_ctx_phase_ms",
-    "fw_ctx_phase_spans", "fw_shard_validate", "fw_shard_pivot", "fw_shard_update", "fw_shard_update_ex", "fw_shard_update_pair", "fw_shard_update_group",
+    "fw_ctx_phase_spans",
+    "fw_multi_create", "fw_multi_unique_id", "fw_multi_create_rank", "fw_multi_destroy", "fw_multi_last_error",
+    "fw_multi_sync", "fw_multi_optimum", "fw_multi_download", "fw_multi_solve_edges", "fw_multi_solve",
+    "fw_multi_alloc", "fw_multi_upload", "fw_multi_solve_resident", "fw_multi_local_shards", "fw_multi_shard",
+    "fw_multi_last_solve_ms", "fw_multi_set_profiling", "fw_multi_phase_ms", "fw_multi_record_row_snapshots",
+    "fw_multi_download_sink", "fw_multi_plan", "fw_multi_resolve", "fw_multi_download_local",
     "fw_paths", "fw_paths_device", "fw_build_matrix_device", "fw_state_create", "fw_state_destroy",
     "fw_state_sync", "fw_state_optimum", "fw_state_download", "fw_solve_edges",
     "fw_ctx_last_error", "fw_solve_device_range", "fw_ctx_set_row_snapshot_sink",
     "fw_tables_create", "fw_tables_destroy", "fw_tables_paths",
 )
+
+
+class PlanOp(ctypes.Structure):
+    """fw_plan_op (include/fwgpu.h): one operation of the multi-GPU schedule."""
+    _fields_ = [(f, ctypes.c_int32) for f in ("kind", "rank", "lane", "b0", "nb", "buf", "row_lo", "row_n",
+                                              "ex_lo", "ex_n", "grp_lo")]
+
+
+class ShardInfo(ctypes.Structure):
+    """fw_shard_info (include/fwgpu.h)."""
+    _fields_ = [(f, ctypes.c_int32) for f in ("device", "rank", "world", "rows", "n_padded", "cyclic_rows", "group")] + \
+               [("ld", ctypes.c_int64), ("d_rate", ctypes.c_void_p), ("d_next", ctypes.c_void_p)]
+
+
+OP_PIVOT, OP_APPLY, OP_BCAST, OP_A_DONE, OP_WAIT_A, OP_B_DONE, OP_WAIT_B = 1, 2, 3, 4, 5, 6, 7
 
 
 class FwError(RuntimeError):
@@ -73,18 +93,52 @@ def load():
     L.fw_ctx_phase_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     L.fw_ctx_phase_spans.restype = i64
     L.fw_ctx_phase_spans.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), i64]
-    L.fw_shard_validate.restype = ctypes.c_int
-    L.fw_shard_validate.argtypes = [vp, i32, i32, i32, i64, vp, vp]
-    L.fw_shard_pivot.restype = ctypes.c_int
-    L.fw_shard_pivot.argtypes = [vp, i32, i32, i32, i64, vp, vp, i32, vp]
-    L.fw_shard_update.restype = ctypes.c_int
-    L.fw_shard_update.argtypes = [vp, i32, i32, i32, i64, vp, vp, i32, vp]
-    L.fw_shard_update_ex.restype = ctypes.c_int
-    L.fw_shard_update_ex.argtypes = [vp, i32, i32, i32, i64, vp, vp, i32, vp, i32, i32]
-    L.fw_shard_update_pair.restype = ctypes.c_int
-    L.fw_shard_update_pair.argtypes = [vp, i32, i32, i32, i64, vp, vp, i32, vp, vp, i32, i32, i32]
-    L.fw_shard_update_group.restype = ctypes.c_int
-    L.fw_shard_update_group.argtypes = [vp, i32, i32, i32, i64, vp, vp, i32, i32, ctypes.POINTER(vp), i32, i32, i32]
+    L.fw_multi_create.restype = ctypes.c_int
+    L.fw_multi_create.argtypes = [i32, vp, ctypes.POINTER(vp)]
+    L.fw_multi_unique_id.restype = ctypes.c_int
+    L.fw_multi_unique_id.argtypes = [vp]
+    L.fw_multi_create_rank.restype = ctypes.c_int
+    L.fw_multi_create_rank.argtypes = [i32, i32, i32, vp, ctypes.POINTER(vp)]
+    L.fw_multi_destroy.restype = None
+    L.fw_multi_destroy.argtypes = [vp]
+    L.fw_multi_last_error.restype = ctypes.c_char_p
+    L.fw_multi_last_error.argtypes = [vp]
+    L.fw_multi_sync.restype = ctypes.c_int
+    L.fw_multi_sync.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32]
+    L.fw_multi_optimum.restype = ctypes.c_int
+    L.fw_multi_optimum.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), vp, i32, ctypes.POINTER(i32)]
+    L.fw_multi_download.restype = ctypes.c_int
+    L.fw_multi_download.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.fw_multi_solve_edges.restype = ctypes.c_int
+    L.fw_multi_solve_edges.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.fw_multi_solve.restype = ctypes.c_int
+    L.fw_multi_solve.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.fw_multi_alloc.restype = ctypes.c_int
+    L.fw_multi_alloc.argtypes = [vp, i32, i32]
+    L.fw_multi_upload.restype = ctypes.c_int
+    L.fw_multi_upload.argtypes = [vp, i32, i32, vp, vp]
+    L.fw_multi_solve_resident.restype = ctypes.c_int
+    L.fw_multi_solve_resident.argtypes = [vp]
+    L.fw_multi_local_shards.restype = i32
+    L.fw_multi_local_shards.argtypes = [vp]
+    L.fw_multi_shard.restype = ctypes.c_int
+    L.fw_multi_shard.argtypes = [vp, i32, ctypes.POINTER(ShardInfo)]
+    L.fw_multi_last_solve_ms.restype = ctypes.c_int
+    L.fw_multi_last_solve_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
+    L.fw_multi_set_profiling.restype = ctypes.c_int
+    L.fw_multi_set_profiling.argtypes = [vp, i32]
+    L.fw_multi_phase_ms.restype = ctypes.c_int
+    L.fw_multi_phase_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
+    L.fw_multi_record_row_snapshots.restype = ctypes.c_int
+    L.fw_multi_record_row_snapshots.argtypes = [vp, i32]
+    L.fw_multi_download_sink.restype = ctypes.c_int
+    L.fw_multi_download_sink.argtypes = [vp, i32, i32, vp]
+    L.fw_multi_resolve.restype = ctypes.c_int
+    L.fw_multi_resolve.argtypes = [vp]
+    L.fw_multi_download_local.restype = ctypes.c_int
+    L.fw_multi_download_local.argtypes = [vp, i32, vp, vp]
+    L.fw_multi_plan.restype = i64
+    L.fw_multi_plan.argtypes = [i32, i32, i32, i32, i32, ctypes.POINTER(PlanOp), i64]
     L.fw_paths.restype = ctypes.c_int
     L.fw_paths.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, vp, i64]
     L.fw_paths_device.restype = ctypes.c_int

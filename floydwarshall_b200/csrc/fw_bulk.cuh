@@ -35,7 +35,10 @@ struct BulkArgs {
     int32_t *mid;          // nullable
     long long ld;
     int b0;                // first pivot of the (first) k-block (global)
-    int row0;              // global index of local row 0 (row shards; 0 otherwise)
+    // Row shards: this launch sees local rows of a shard starting at local row `row0` of it; local row l of
+    // the shard is global row ((l / cbr) * P + r) * cbr + l % cbr  (cyclic blocks of cbr rows over P ranks;
+    // unsharded: row0 = 0, cbr huge, P = 1, r = 0).  Only the diagonal test needs global rows.
+    int row0, cbr, P, r;
     // One launch applies nb (1 .. BULK_MAXNB) CONSECUTIVE k-blocks [b0, b0 + nb*128) to every selected tile,
     // from per-block snapshot panels:
     int nb;
@@ -248,7 +251,8 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
     }
     {   // the matrix diagonal crosses this tile: hold it as +inf -- o < n is false for every n, it is never
         // written back (chg stays clear), and fma(a, b, -inf) = -inf keeps the filter on its fast path
-        const int gi0 = a.row0 + i0;
+        const int li0 = a.row0 + i0;                                          // a 64-row tile never straddles a cyclic block
+        const int gi0 = ((li0 / a.cbr) * a.P + a.r) * a.cbr + li0 % a.cbr;
         if (gi0 + BULK_TR > j0 && gi0 < j0 + TW) {
 #pragma unroll
             for (int r = 0; r < 8; ++r)

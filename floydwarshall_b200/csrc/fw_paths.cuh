@@ -14,8 +14,8 @@
 // first PATH_LSTACK slots live in local memory, deeper ones in a global overflow
 // area the host provides when a first attempt reports "stack overflow".
 //
-// The tables may be ROW-SHARDED (multi-GPU solve): row x lives in shard x / rows_per
-// at local row x % rows_per; peers are read through NVLink (peer access enabled).
+// The tables may be ROW-SHARDED (multi-GPU solve, cyclic blocks of rows: fw_plan.hpp);
+// peers are read through NVLink (peer access enabled).
 #pragma once
 #include "fw_common.cuh"
 
@@ -28,8 +28,8 @@ struct PathTables {
     const int32_t *init_next[PATH_MAXSHARD], *mid[PATH_MAXSHARD], *csT[PATH_MAXSHARD], *rs[PATH_MAXSHARD];
     long long ld;
     int n;
-    int rows_per;               // rows per shard (>= n when unsharded)
-};
+    int cbr, P;                 // global row x lives on shard (x / cbr) % P at local row (x / (cbr*P)) * cbr + x % cbr
+};                              // (unsharded: cbr >= n, P = 1)
 
 struct PathArgs {
     PathTables t;
@@ -66,8 +66,8 @@ __device__ __forceinline__ long long walk_path(const PathTables &t, int src, int
         const unsigned long long it = (sp < PATH_LSTACK) ? st[sp] : gst[sp - PATH_LSTACK];
         const int kind = (int)(it >> 62);
         const int x = (int)((it >> 31) & 0x7fffffffu), y = (int)(it & 0x7fffffffu);
-        const int sh = x / t.rows_per;
-        const long long off = (long long)(x - sh * t.rows_per) * t.ld + y;
+        const int cb = x / t.cbr, sh = cb % t.P;
+        const long long off = (long long)((cb / t.P) * t.cbr + x % t.cbr) * t.ld + y;
         const int m = (kind == 0) ? t.mid[sh][off] : (kind == 1 ? t.csT[sh][off] : t.rs[sh][off]);
         if (m < 0) {
             if (t.init_next[sh][off] >= 0) {
@@ -121,8 +121,8 @@ __global__ void fw_optimum_kernel(OptimumArgs a) {
     double *o_rate = reinterpret_cast<double *>(a.out);
     long long *o_len = reinterpret_cast<long long *>(a.out + 8);
     int32_t *o_verts = reinterpret_cast<int32_t *>(a.out + 16);
-    const int sh = a.src / a.t.rows_per;
-    *o_rate = a.rate[sh][(long long)(a.src - sh * a.t.rows_per) * a.rate_ld + a.dst];
+    const int cb = a.src / a.t.cbr, sh = cb % a.t.P;
+    *o_rate = a.rate[sh][(long long)((cb / a.t.P) * a.t.cbr + a.src % a.t.cbr) * a.rate_ld + a.dst];
     const int cap = a.cap;
     *o_len = walk_path(a.t, a.src, a.dst, a.max_len, a.gstack, a.gcap,
                        [&](long long pos, int y) { if (pos < cap) o_verts[pos] = y; });

@@ -65,16 +65,18 @@ struct ErrScope {
 
 // ---------------------------------------------------------------- helper kernels
 // flag bit 0: negative rate; bit 1: rate > 0 (off-diagonal) with next < 0
-// Each of `batch` graphs is rows x n (rows == n unless it is a row shard starting at global row row0).
+// Each of `batch` graphs is rows x n (rows == n unless it is a row shard: local row l is then global row
+// ((l / cbr) * P + r) * cbr + l % cbr; rows at or beyond nvalid are padding and not checked).
 __global__ void fw_validate_kernel(const double *rate, const int32_t *next, long long ld, long long stride,
-                                   int rows, int n, int row0, long long total, int *flag) {
+                                   int rows, int n, int cbr, int P, int r, int nvalid, long long total, int *flag) {
     int bad = 0;
     const long long nn = (long long)rows * n;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
          e += (long long)gridDim.x * blockDim.x) {
         const long long g = e / nn, rem = e - g * nn;
         const int i = (int)(rem / n), j = (int)(rem - (long long)i * n);
-        if (row0 + i == j) continue;  // the diagonal is never read (Algorithms.hs:50,54)
+        const int gi = ((i / cbr) * P + r) * cbr + i % cbr;
+        if (gi == j || gi >= nvalid || j >= nvalid) continue;  // the diagonal is never read (Algorithms.hs:50,54)
         const long long off = g * stride + (long long)i * ld + j;
         const double v = rate[off];
         if (v < 0.0) bad |= 1;
@@ -340,15 +342,18 @@ void launch_panel(fw_ctx *c, const fw::PanelArgs &p, int jobs, bool paths, cudaS
 
 // Domain check (synchronises the stream once).
 int validate_device(fw_ctx *c, const double *rate, const int32_t *next, long long ld, long long stride,
-                    int batch, int n, int rows = -1, int row0 = 0) {
+                    int batch, int n, int rows = -1, int cbr = 1 << 30, int P = 1, int r = 0, int nvalid = -1,
+                    bool sync = true) {
     if (rows < 0) rows = n;
+    if (nvalid < 0) nvalid = n;
     CU(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->stream));
     const long long total = (long long)batch * rows * n;
-    fw_validate_kernel<<<grid_for(total, c->sm_count), 256, 0, (c->cur ? c->cur : c->stream)>>>(rate, next, ld, stride, rows, n, row0,
-                                                                             total, c->d_flag);
+    fw_validate_kernel<<<grid_for(total, c->sm_count), 256, 0, (c->cur ? c->cur : c->stream)>>>(rate, next, ld, stride, rows, n, cbr, P, r,
+                                                                             nvalid, total, c->d_flag);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (!sync) return FW_OK;            // the caller collects h_flag of several devices after one round of syncs
     CU(cudaStreamSynchronize(c->stream));
     if (*c->h_flag & 1) return fail(FW_ERR_DOMAIN, "rate matrix holds a negative entry");
     if (*c->h_flag & 2) return fail(FW_ERR_DOMAIN, "rate > 0 with next < 0 (inconsistent next-hop matrix)");
@@ -431,7 +436,7 @@ int solve_blocked(fw_ctx *c, int npad, long long ld, double *rate, int32_t *next
     cudaStream_t T = (c->overlap && c->side_stream) ? c->side_stream : c->stream;
     const bool two = (T != S);
     fw::BulkArgs g;
-    g.rate = rate; g.next = next; g.mid = mid; g.ld = ld; g.row0 = 0; g.ldc = npad; g.ldw = npad;
+    g.rate = rate; g.next = next; g.mid = mid; g.ld = ld; g.row0 = 0; g.cbr = 1 << 30; g.P = 1; g.r = 0; g.ldc = npad; g.ldw = npad;
     auto use_sets = [&](int s0) {
         for (int i = 0; i < GMAX; ++i) {
             const int s = s0 + (i < gsz ? i : 0);
@@ -948,7 +953,7 @@ fw::PathTables one_shard_tables(int n, long long ld, const int32_t *init_next, c
                                 const int32_t *rs) {
     fw::PathTables t;
     for (int i = 0; i < fw::PATH_MAXSHARD; ++i) { t.init_next[i] = init_next; t.mid[i] = mid; t.csT[i] = csT; t.rs[i] = rs; }
-    t.ld = ld; t.n = n; t.rows_per = n > 0 ? n : 1;
+    t.ld = ld; t.n = n; t.cbr = n > 0 ? n : 1; t.P = 1;
     return t;
 }
 
@@ -1322,223 +1327,9 @@ int fw_solve_edges(fw_ctx *c, int32_t n, const int32_t *ccy, int32_t m, const in
     return FW_OK;
 }
 
-/* ---- row-sharded building blocks (multi-GPU) ------------------------------- */
-static int shard_args_ok(int32_t n, int32_t row0, int32_t rows, int64_t ld, const void *rate, const void *next,
-                         int32_t b0, const void *Rw) {
-    if (n <= 0 || rows <= 0 || row0 < 0 || b0 < 0 || !rate || !next || !Rw) return 0;
-    if (n % FW_B || rows % FW_B || row0 % FW_B || b0 % FW_B) return 0;
-    if (row0 + rows > n || b0 >= n || ld < n || ld % 4) return 0;
-    if (((uintptr_t)rate & 15) || ((uintptr_t)next & 15) || ((uintptr_t)Rw & 15)) return 0;
-    return 1;
-}
-
-int fw_shard_validate(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, const double *d_rate,
-                      const int32_t *d_next) {
-    ErrScope es0__(c);
-    if (!c || n <= 0 || rows <= 0 || !d_rate || !d_next || ld < n)
-        return fail(FW_ERR_INVALID, "fw_shard_validate: bad argument");
-    FW_ENTER(c);
-    CU(cudaSetDevice(c->device));
-    return validate_device(c, d_rate, d_next, ld, 0, 1, n, rows, row0);
-}
-
-int fw_shard_pivot(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
-                   int32_t *d_next, int32_t b0, double *d_Rw) {
-    ErrScope es0__(c);
-    if (!c || !shard_args_ok(n, row0, rows, ld, d_rate, d_next, b0, d_Rw))
-        return fail(FW_ERR_INVALID, "fw_shard_pivot: bad argument (sizes must be multiples of 128, 16-byte aligned)");
-    if (b0 < row0 || b0 >= row0 + rows) return fail(FW_ERR_INVALID, "fw_shard_pivot: this shard does not own k-block b0");
-    FW_ENTER(c);
-    CU(cudaSetDevice(c->device));
-    c->cur = nullptr;
-    int rc;
-    if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
-    if ((rc = c->Cp[0].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
-    if ((rc = c->NCp[0].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
-    c->launches = 0;
-    recycle_spans(c);
-    const int blk_r0 = b0 - row0;
-    fw::TileArgs t;
-    t.rate = d_rate; t.next = d_next; t.mid = nullptr; t.csT = nullptr; t.rs = nullptr;
-    t.ld = ld; t.batch_stride = 0; t.b0 = b0; t.r0 = blk_r0; t.nv = FW_B;
-    t.Cp = c->Cp[0].p; t.ldc = rows; t.NCp = c->NCp[0].p; t.Rw = d_Rw; t.ldw = n;
-    {
-        PhaseTimer pt(c, 0);
-        fw::fw_tile_kernel<false><<<1, 512, fw::tile_smem_bytes(false), c->stream>>>(t);
-    }
-    c->launches++;
-    if (n > FW_B) {
-        fw::PanelArgs p;
-        p.rate = d_rate; p.next = d_next; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
-        p.ld = ld; p.npad = n; p.b0 = b0; p.rows = rows; p.blk_r0 = blk_r0; p.skip_r0 = blk_r0; p.skipn = FW_B;
-        p.Cp = c->Cp[0].p; p.ldc = rows; p.NCp = c->NCp[0].p; p.Rw = d_Rw; p.ldw = n;
-        PhaseTimer pt(c, 2);
-        launch_panel<false>(c, p, n - FW_B, false, c->stream);
-    }
-    CU(cudaGetLastError());
-    return FW_OK;
-}
-
-/* mode 0: every local row outside the k-block; mode 1: ONLY the 128 local rows starting at lr0;
- * mode 2: every local row outside the k-block and outside the 128 rows starting at lr0. */
-int fw_shard_update_ex(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
-                       int32_t *d_next, int32_t b0, const double *d_Rw, int32_t mode, int32_t lr0) {
-    ErrScope es0__(c);
-    if (!c || !shard_args_ok(n, row0, rows, ld, d_rate, d_next, b0, d_Rw))
-        return fail(FW_ERR_INVALID, "fw_shard_update: bad argument (sizes must be multiples of 128, 16-byte aligned)");
-    if (mode < 0 || mode > 2 || (mode != 0 && (lr0 < 0 || lr0 % FW_B || lr0 + FW_B > rows)))
-        return fail(FW_ERR_INVALID, "fw_shard_update_ex: bad mode / row range");
-    FW_ENTER(c);
-    CU(cudaSetDevice(c->device));
-    c->cur = nullptr;
-    int rc;
-    if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
-    if ((rc = c->Cp[0].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
-    if ((rc = c->NCp[0].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
-    const bool owner = (b0 >= row0 && b0 < row0 + rows);
-    const int blk_r0 = owner ? b0 - row0 : -1;
-    if (mode != 0 && owner && lr0 == blk_r0) return fail(FW_ERR_INVALID, "fw_shard_update_ex: lr0 is the k-block itself");
-    c->launches = 0;
-    recycle_spans(c);
-    // The rows to process form the sub-shard [v0, v0 + vrows) minus one skip range [s0, s0 + sn)  (local rows)
-    int v0 = 0, vrows = rows, s0 = NOSKIP, sn = 0;
-    if (mode == 1) {
-        v0 = lr0; vrows = FW_B;
-    } else {
-        if (owner) { s0 = blk_r0; sn = FW_B; }
-        if (mode == 2) {
-            if (!owner) { s0 = lr0; sn = FW_B; }
-            else if (lr0 == blk_r0 + FW_B) { sn = 2 * FW_B; }
-            else if (lr0 + FW_B == blk_r0) { s0 = lr0; sn = 2 * FW_B; }
-            else return fail(FW_ERR_INVALID, "fw_shard_update_ex: mode 2 needs lr0 adjacent to the k-block rows");
-        }
-    }
-    const int rows_out = vrows - sn;
-    if (rows_out <= 0 || n <= FW_B) return FW_OK;
-    // kernels see the sub-shard as a shard of its own: pointers and row origin shifted by v0
-    double *rate_v = d_rate + (long long)v0 * ld;
-    int32_t *next_v = d_next + (long long)v0 * ld;
-    double *cp_v = c->Cp[0].p + v0;                       // CpT[kk*ldc + i]
-    int32_t *ncp_v = c->NCp[0].p + (long long)v0 * FW_B;  // NCp[i*B + kk]
-    const int s0v = (s0 == NOSKIP) ? NOSKIP : s0 - v0;
-    fw::PanelArgs p;
-    p.rate = rate_v; p.next = next_v; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
-    p.ld = ld; p.npad = n; p.b0 = b0; p.rows = vrows; p.blk_r0 = NOSKIP; p.skip_r0 = s0v; p.skipn = sn;
-    p.Cp = cp_v; p.ldc = rows; p.NCp = ncp_v; p.Rw = const_cast<double *>(d_Rw); p.ldw = n;
-    {
-        PhaseTimer pt(c, 1);
-        launch_panel<true>(c, p, rows_out, false, c->stream);
-    }
-    fw::BulkArgs g;
-    g.rate = rate_v; g.next = next_v; g.mid = nullptr; g.ld = ld; g.b0 = b0; g.row0 = row0 + v0;
-    g.nb = 1; g.half_r0 = NOSKIP; g.half_c0 = NOSKIP;
-    for (int i = 0; i < fw::BULK_MAXNB; ++i) { g.CpT[i] = cp_v; g.NCp[i] = ncp_v; g.Rw[i] = d_Rw; }
-    g.ldc = rows; g.ldw = n;
-    g.row_lo = 0; g.rskip0 = (s0v == NOSKIP) ? NOSKIP : s0v / 64; g.rskipn = sn / 64;
-    g.col_lo = 0; g.cskip0 = b0 / 64; g.cskipn = 2;
-    launch_bulk(c, g, n / 64 - 2, rows_out / 64);
-    CU(cudaGetLastError());
-    return FW_OK;
-}
-
-int fw_shard_update_group(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
-                          int32_t *d_next, int32_t b0, int32_t nb, const double *const *d_Rw, int32_t mode,
-                          int32_t lr0, int32_t lrn) {
-    ErrScope es0__(c);
-    if (!c || !d_Rw || nb < 1 || nb > fw::BULK_MAXNB || !shard_args_ok(n, row0, rows, ld, d_rate, d_next, b0, d_Rw[0]))
-        return fail(FW_ERR_INVALID, "fw_shard_update_group: bad argument (sizes must be multiples of 128, 16-byte aligned)");
-    for (int i = 0; i < nb; ++i)
-        if (!d_Rw[i] || ((uintptr_t)d_Rw[i] & 15)) return fail(FW_ERR_INVALID, "fw_shard_update_group: bad panel pointer");
-    const int gw = nb * FW_B;                       // width of the group in rows / columns
-    if (b0 + gw > n) return fail(FW_ERR_INVALID, "fw_shard_update_group: the k-blocks run past n");
-    if (mode < 0 || mode > 2 || (mode != 0 && (lr0 < 0 || lrn <= 0 || lr0 % FW_B || lrn % FW_B || lr0 + lrn > rows)))
-        return fail(FW_ERR_INVALID, "fw_shard_update_group: bad mode / row range");
-    // the blocks' own rows, clipped to this shard (local rows [g0, g0 + gn))
-    int g0 = b0 - row0, g1 = b0 + gw - row0;
-    if (g0 < 0) g0 = 0;
-    if (g1 > rows) g1 = rows;
-    const int gn = g1 > g0 ? g1 - g0 : 0;
-    FW_ENTER(c);
-    CU(cudaSetDevice(c->device));
-    c->cur = nullptr;
-    int rc;
-    if ((rc = set_kernel_attrs(c)) != FW_OK) return rc;
-    for (int set = 0; set < nb; ++set) {
-        if ((rc = c->Cp[set].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
-        if ((rc = c->NCp[set].ensure((size_t)rows * FW_B)) != FW_OK) return rc;
-    }
-    c->launches = 0;
-    recycle_spans(c);
-    // rows to process: the sub-shard [v0, v0 + vrows) minus one skip range [s0, s0 + sn)   (local rows)
-    int v0 = 0, vrows = rows, s0 = NOSKIP, sn = 0;
-    if (mode == 1) {
-        if (gn > 0 && lr0 < g0 + gn && g0 < lr0 + lrn)
-            return fail(FW_ERR_INVALID, "fw_shard_update_group: mode 1 rows overlap the k-blocks' own rows");
-        v0 = lr0; vrows = lrn;
-    } else {
-        if (gn > 0) { s0 = g0; sn = gn; }
-        if (mode == 2) {
-            if (gn == 0) { s0 = lr0; sn = lrn; }
-            else if (lr0 == g0 + gn) { sn = gn + lrn; }
-            else if (lr0 + lrn == g0) { s0 = lr0; sn = gn + lrn; }
-            else return fail(FW_ERR_INVALID, "fw_shard_update_group: mode 2 needs the row range adjacent to the k-blocks' rows");
-        }
-    }
-    const int rows_out = vrows - sn;
-    if (rows_out <= 0) return FW_OK;
-    double *rate_v = d_rate + (long long)v0 * ld;
-    int32_t *next_v = d_next + (long long)v0 * ld;
-    const int s0v = (s0 == NOSKIP) ? NOSKIP : s0 - v0;
-    fw::BulkArgs g;
-    g.rate = rate_v; g.next = next_v; g.mid = nullptr; g.ld = ld; g.b0 = b0; g.row0 = row0 + v0;
-    g.ldc = rows; g.ldw = n;
-    for (int i = 0; i < fw::BULK_MAXNB; ++i) {
-        const int set = i < nb ? i : nb - 1;
-        g.CpT[i] = c->Cp[set].p + v0;                         // CpT[kk*ldc + i]
-        g.NCp[i] = c->NCp[set].p + (long long)v0 * FW_B;      // NCp[i*B + kk]
-        g.Rw[i] = d_Rw[set];
-    }
-    g.row_lo = 0; g.rskip0 = (s0v == NOSKIP) ? NOSKIP : s0v / 64; g.rskipn = sn / 64;
-    g.half_r0 = NOSKIP;                             // no tile of these rows lies in a row strip of the group
-    for (int blk = 0; blk < nb; ++blk) {
-        if (blk > 0) {
-            // blocks 0 .. blk-1 on the column strip of block blk, so that its column panel can run
-            g.nb = blk; g.half_c0 = NOSKIP;
-            g.col_lo = (b0 + blk * FW_B) / 64; g.cskip0 = NOSKIP; g.cskipn = 0;
-            launch_bulk(c, g, 2, rows_out / 64);
-        }
-        fw::PanelArgs p;
-        p.rate = rate_v; p.next = next_v; p.mid = nullptr; p.csT = nullptr; p.rs = nullptr;
-        p.ld = ld; p.npad = n; p.b0 = b0 + blk * FW_B; p.rows = vrows; p.blk_r0 = NOSKIP; p.skip_r0 = s0v; p.skipn = sn;
-        p.Cp = const_cast<double *>(g.CpT[blk]); p.ldc = rows; p.NCp = const_cast<int32_t *>(g.NCp[blk]);
-        p.Rw = const_cast<double *>(d_Rw[blk]); p.ldw = n;
-        PhaseTimer pt(c, 1);
-        launch_panel<true>(c, p, rows_out, false, c->stream);
-    }
-    // all nb blocks for every other tile from one load; the column strip of block i < nb-1 took blocks 0..i in
-    // the strip launches and its column panel and starts at block i+1; the last block's strip is complete
-    g.nb = nb; g.half_c0 = (nb > 1) ? b0 / 64 : NOSKIP;
-    g.col_lo = 0; g.cskip0 = (b0 + (nb - 1) * FW_B) / 64; g.cskipn = 2;
-    launch_bulk(c, g, n / 64 - 2, rows_out / 64);
-    CU(cudaGetLastError());
-    return FW_OK;
-}
-
-int fw_shard_update_pair(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
-                         int32_t *d_next, int32_t b0, const double *d_Rw0, const double *d_Rw1, int32_t mode,
-                         int32_t lr0, int32_t lrn) {
-    ErrScope es0__(c);
-    const double *rw[2] = {d_Rw0, d_Rw1};
-    return fw_shard_update_group(c, n, row0, rows, ld, d_rate, d_next, b0, 2, rw, mode, lr0, lrn);
-}
-
-int fw_shard_update(fw_ctx *c, int32_t n, int32_t row0, int32_t rows, int64_t ld, double *d_rate,
-                    int32_t *d_next, int32_t b0, const double *d_Rw) {
-    ErrScope es0__(c);
-    return fw_shard_update_ex(c, n, row0, rows, ld, d_rate, d_next, b0, d_Rw, 0, 0);
-}
-
 }  // extern "C"
+
+#include "fw_multi.cuh"
 
 #ifdef FW_BULK_STATS
 // experiment build only: read (and optionally clear) the bulk kernel's fast-path counters

@@ -197,52 +197,104 @@ int fw_state_optimum(fw_state *st, int32_t src, int32_t dst, double *rate, int32
 /* Optional full read-back (tests): host rate[n*n] and/or next[n*n]. */
 int fw_state_download(fw_state *st, double *rate, int32_t *next);
 
-/* ---- row-sharded building blocks (one shard per GPU) ----------------------
- * The multi-GPU solve keeps rows [row0, row0+rows) of the n x n
- * matrix on each GPU (n, row0, rows multiples of FW_TILE; ld % 4 == 0).  For
- * every k-block b0 = 0, 128, ...:
- *   owner of rows [b0, b0+128):  fw_shard_pivot  -> fills d_Rw (128 x n, the
- *        step-k snapshots of the pivot rows) from its diagonal tile + row panel
- *   caller broadcasts d_Rw from the owner to all ranks (NCCL)
- *   every rank:                  fw_shard_update -> column panel + bulk on its rows
- * Next-hops never cross ranks (NX[i][j] <- NX[i][k] is row-local).  All calls
- * are asynchronous on the context's stream.  No exact-path tables here. */
-int fw_shard_validate(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
-                      const double *d_rate, const int32_t *d_next);
-int fw_shard_pivot(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
-                   double *d_rate, int32_t *d_next, int32_t b0, double *d_Rw);
-int fw_shard_update(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
-                    double *d_rate, int32_t *d_next, int32_t b0, const double *d_Rw);
-/* Look-ahead variant: mode 0 = fw_shard_update; mode 1 = ONLY the 128 local rows starting at
- * lr0 (the next k-block's pivot rows, so its owner can factor them early on a second stream);
- * mode 2 = everything mode 0 does EXCEPT those 128 rows (lr0 must be adjacent to the k-block
- * rows when the shard owns them). */
-int fw_shard_update_ex(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
-                       double *d_rate, int32_t *d_next, int32_t b0, const double *d_Rw,
-                       int32_t mode, int32_t lr0);
-/* Two CONSECUTIVE k-blocks b0, b0+128 in one call, so that the bulk kernel loads every tile of the
- * shard once per 256 steps (the single-GPU solve's pairing): column panel of b0, bulk(b0) on the
- * column strip of b0+128, column panel of b0+128, then one fused bulk launch.  d_Rw0 / d_Rw1 are the
- * row-snapshot panels of the two blocks (both pivoted and broadcast before the call).  Needs row0,
- * rows, b0 multiples of 256.  Rows: mode 0 = every local row outside the pair's own 256 rows;
- * mode 1 = ONLY the lrn local rows starting at lr0; mode 2 = mode 0 minus those rows (adjacent to
- * the pair's rows when the shard owns them).  The pair's own rows are the owner's business:
- * fw_shard_pivot(b0), fw_shard_update_ex(b0, mode 1, rows of b0+128), fw_shard_pivot(b0+128) before
- * the broadcasts, fw_shard_update_ex(b0+128, mode 1, rows of b0) after them. */
-int fw_shard_update_pair(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
-                         double *d_rate, int32_t *d_next, int32_t b0, const double *d_Rw0,
-                         const double *d_Rw1, int32_t mode, int32_t lr0, int32_t lrn);
-/* nb (1..8) CONSECUTIVE k-blocks b0, b0+128, ... in one call (fw_shard_update_pair is nb = 2): for each
- * block in turn its column panel, preceded by one fused launch that brings the block's column strip up
- * to date with the earlier blocks of the call, then one fused bulk launch of all nb blocks.  d_Rw[i] is
- * the row-snapshot panel of block i (HOST array of nb device pointers).  Rows: mode 0 = every local row
- * outside [b0, b0 + nb*128); mode 1 = ONLY the lrn local rows starting at lr0 (any rows that do not
- * intersect the blocks' own); mode 2 = mode 0 minus those rows (adjacent to the blocks' rows when the
- * shard owns them).  The blocks' own rows are the owner's business, before and after the broadcasts
- * (floydwarshall_b200/sharded.py: run_schedule_lookahead_groups). */
-int fw_shard_update_group(fw_ctx *ctx, int32_t n, int32_t row0, int32_t rows, int64_t ld,
-                          double *d_rate, int32_t *d_next, int32_t b0, int32_t nb,
-                          const double *const *d_Rw, int32_t mode, int32_t lr0, int32_t lrn);
+/* ---- multi-GPU solve (config C5) ------------------------------
+ * ONE object drives the row-sharded solve; the k-block schedule, the streams and
+ * the pivot-panel broadcast all live inside the library, so that the reference's
+ * single in-process call (Algorithms.hs:19-20, sole caller ProcessRequests.hs:82-84)
+ * reaches every GPU of the box.  Two ways to build it:
+ *   fw_multi_create       one process drives ndev GPUs (devices[] or NULL = 0..ndev-1).
+ *                         The same device may be named several times ("virtual ranks":
+ *                         tests on a one-GPU box; transport is then device copies).
+ *   fw_multi_create_rank  one process per GPU (torchrun / MPI style): this process
+ *                         holds shard `rank` of `world` on `device`; nccl_id = the
+ *                         128 bytes fw_multi_unique_id() produced on rank 0.
+ * Transport of the 128 x n row-snapshot panel: NCCL broadcast (ncclCommInitAll /
+ * ncclCommInitRank; libnccl is dlopen'ed on first use) or, single process only,
+ * copy-engine peer copies (FW_MULTI_TRANSPORT=nccl|p2p; default p2p when every peer
+ * is reachable, else nccl).
+ *
+ * Sharding: rows in cyclic blocks of one k-block group (ownership of the pivot
+ * rows rotates over the ranks; FW_MULTI_CYCLIC=0: contiguous row blocks); k-blocks
+ * in groups of up to 8 per fused bulk launch (FW_MULTI_GROUP=1|2|4|8).  n is padded
+ * internally; any n >= 1 works.
+ *
+ * State: fw_multi_sync is syncMatrix on an OutSync state (ProcessRequests.hs:82-84):
+ * the cache goes up in COO form, every shard runs buildMatrix for its rows and the
+ * solve; the optimised matrix and its exact-path tables STAY sharded in HBM.
+ * fw_multi_optimum reads one entry + its `_path` (Algorithms.hs:74-75) across the
+ * shards (single-process mode; peers are read over NVLink).  fw_multi_download
+ * copies any row range to the host (rank mode: local rows only are written, other
+ * rows of the range are left untouched). */
+typedef struct fw_multi fw_multi;
+int fw_multi_create(int32_t ndev, const int32_t *devices, fw_multi **out);
+int fw_multi_unique_id(void *id128);
+int fw_multi_create_rank(int32_t device, int32_t rank, int32_t world, const void *nccl_id128,
+                         fw_multi **out);
+void fw_multi_destroy(fw_multi *m);
+const char *fw_multi_last_error(fw_multi *m);
+int fw_multi_sync(fw_multi *m, int32_t n, const int32_t *ccy, int32_t n_edges, const int32_t *src,
+                  const int32_t *dst, const double *val, int32_t want_paths);
+/* The last fw_multi_sync once more from the COO that is still on the devices (buildMatrix + runAlgo, nothing
+ * crosses PCIe): the benchmark's "inputs resident in HBM" step. */
+int fw_multi_resolve(fw_multi *m);
+int fw_multi_optimum(fw_multi *m, int32_t src, int32_t dst, double *rate, int32_t *path,
+                     int32_t cap, int32_t *path_len);
+int fw_multi_download(fw_multi *m, int32_t row0, int32_t rows, double *rate, int32_t *next,
+                      int32_t *init_next, int32_t *mid, int32_t *csT, int32_t *rs);
+/* floydWarshall in one call on all GPUs (single process): map in COO form in, dense host matrices out. */
+int fw_multi_solve_edges(fw_multi *m, int32_t n, const int32_t *ccy, int32_t n_edges,
+                         const int32_t *src, const int32_t *dst, const double *val, double *rate,
+                         int32_t *next, int32_t *init_next, int32_t *mid, int32_t *csT, int32_t *rs);
+/* Dense host matrices in place (runAlgo only): rows go up to their shards, the solve runs, rows come back. */
+int fw_multi_solve(fw_multi *m, int32_t n, double *rate, int32_t *next, int32_t *mid, int32_t *csT,
+                   int32_t *rs);
+/* Resident workflow for benchmarks and tests: allocate the shards for order n, let the caller fill them
+ * (fw_multi_upload: host rows -> shards; or device pointers from fw_multi_shard), then solve in place. */
+int fw_multi_alloc(fw_multi *m, int32_t n, int32_t want_paths);
+int fw_multi_upload(fw_multi *m, int32_t row0, int32_t rows, const double *rate, const int32_t *next);
+int fw_multi_solve_resident(fw_multi *m);
+/* Local shard i (0 .. nlocal-1): its device, rank, local rows, leading dimension and device pointers.
+ * Local row l of rank r is global row  ((l / cyclic_rows) * world + r) * cyclic_rows + l % cyclic_rows. */
+typedef struct fw_shard_info {
+    int32_t device, rank, world, rows, n_padded, cyclic_rows, group;
+    int64_t ld;
+    double *d_rate;
+    int32_t *d_next;
+} fw_shard_info;
+int32_t fw_multi_local_shards(fw_multi *m);
+/* Local shard i as it lies in HBM (rows x n_padded, local row order) into host buffers; either may be NULL. */
+int fw_multi_download_local(fw_multi *m, int32_t i, double *rate, int32_t *next);
+int fw_multi_shard(fw_multi *m, int32_t i, fw_shard_info *out);
+/* Device time of the last solve (CUDA events, max over the local shards), kernel launches issued, and the
+ * bulk kernel's share (per-launch events; only when profiling was on during the solve). */
+int fw_multi_last_solve_ms(fw_multi *m, double *ms, int64_t *launches);
+int fw_multi_set_profiling(fw_multi *m, int32_t on);
+int fw_multi_phase_ms(fw_multi *m, double ms[4], int64_t count[4]);
+/* Verification hook (as fw_ctx_set_row_snapshot_sink): when on, every shard keeps, for the pivot rows it
+ * owns, the row as its step began; fw_multi_download_sink copies a row range of them to the host. */
+int fw_multi_record_row_snapshots(fw_multi *m, int32_t on);
+int fw_multi_download_sink(fw_multi *m, int32_t row0, int32_t rows, double *rows_out);
+
+/* The schedule as data: operations of the WHOLE job in issue order, for a matrix of (padded) order n on
+ * `world` ranks with k-blocks of `block` pivots in groups of `group`, rows in cyclic blocks of
+ * cyclic_rows.  This is what the executor inside fw_multi_* issues; tests replay it with a CPU model of
+ * the same operations.  Returns the number of operations (may exceed cap; none written beyond cap), < 0 on a
+ * bad layout.  Pure host code: works without a GPU. */
+#define FW_OP_PIVOT 1   /* rank's local rows [row_lo, +row_n) = pivot rows b0..: diagonal tile + row panel -> Rw[buf] */
+#define FW_OP_APPLY 2   /* rank's local rows [row_lo, +row_n) minus [ex_lo, +ex_n) take k-blocks b0 .. b0+nb*block from Rw[buf..];
+                           a row in the blocks' own rows (local rows from grp_lo, block i) takes only blocks i+1.. */
+#define FW_OP_BCAST 3   /* Rw[buf] goes from `rank` to every rank (lane B) */
+#define FW_OP_A_DONE 4  /* rank: record "main lane done" */
+#define FW_OP_WAIT_A 5  /* rank: look-ahead lane waits for the last A_DONE */
+#define FW_OP_B_DONE 6  /* rank: record "look-ahead lane done" */
+#define FW_OP_WAIT_B 7  /* rank: main lane waits for the last B_DONE */
+typedef struct fw_plan_op {
+    int32_t kind, rank, lane; /* lane 0 = main (A), 1 = look-ahead (B) */
+    int32_t b0, nb, buf;
+    int32_t row_lo, row_n, ex_lo, ex_n, grp_lo;
+} fw_plan_op;
+int64_t fw_multi_plan(int32_t n, int32_t world, int32_t block, int32_t group, int32_t cyclic_rows,
+                      fw_plan_op *ops, int64_t cap);
 
 /* Block until everything queued on the context's stream has finished and
  * report any asynchronous failure (incl. FW_ERR_DOMAIN of *_device calls). */
