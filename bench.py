@@ -657,8 +657,7 @@ def run_multi(args):
             barrier()
             t0 = time.perf_counter()
             ms.sync(n, ccy, src, dst, val, paths=False)
-            for i in range(nloc):
-                ms.download_local(i, bufs[i][0].data_ptr(), bufs[i][1].data_ptr())
+            ms.download_locals([b[0].data_ptr() for b in bufs], [b[1].data_ptr() for b in bufs])
             barrier()
             ts.append(time.perf_counter() - t0)
         te = torch.tensor([ts[-1]], dtype=torch.float64, device=dev)
@@ -668,7 +667,7 @@ def run_multi(args):
         e2e = {"value": float(n) ** 3 / float(te.item()), "unit": UNIT,
                "h2d_bytes_per_step": coo_bytes * eff_world, "d2h_bytes_per_step": info.n_padded * info.n_padded * 12,
                "ms_per_step": float(te.item()) * 1e3,
-               "api": "fw_multi_sync (rate map in COO form from host arrays) + fw_multi_download_local (every shard's "
+               "api": "fw_multi_sync (rate map in COO form from host arrays) + fw_multi_download_locals (every shard's "
                       "rows into pinned host buffers)"}
         del bufs
         if single:
@@ -713,8 +712,9 @@ def run_multi(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(n), "n": n, "seed": SEED + 1, "k_block": 128,
-                       "processes": "one process drives all GPUs (fw_multi_create, copy-engine panel transport)" if single
-                       else "one process per GPU (fw_multi_create_rank, NCCL broadcast)",
+                       "processes": "one process drives all GPUs (fw_multi_create)" if single
+                       else "one process per GPU (fw_multi_create_rank; NCCL bootstraps the ranks)",
+                       "panel_transport": ms.transport(),
                        "sharding": f"rows in cyclic blocks of {info.cyclic_rows} over {eff_world} ranks ({rows} rows per rank); "
                                    f"per k-block the 128 x {info.n_padded} fp64 pivot-row snapshot panel "
                                    f"({128 * info.n_padded * 8 / 2**20:.0f} MiB) goes from its owner to every rank",

@@ -32,6 +32,7 @@ SYMBOLS = (
     "fw_multi_alloc", "fw_multi_upload", "fw_multi_solve_resident", "fw_multi_local_shards", "fw_multi_shard",
     "fw_multi_last_solve_ms", "fw_multi_set_profiling", "fw_multi_phase_ms", "fw_multi_record_row_snapshots",
     "fw_multi_download_sink", "fw_multi_plan", "fw_multi_resolve", "fw_multi_download_local",
+    "fw_multi_download_locals", "fw_multi_transport",
     "fw_paths", "fw_paths_device", "fw_build_matrix_device", "fw_state_create", "fw_state_destroy",
     "fw_state_sync", "fw_state_optimum", "fw_state_download", "fw_solve_edges",
     "fw_ctx_last_error", "fw_solve_device_range", "fw_ctx_set_row_snapshot_sink",
@@ -137,6 +138,10 @@ def load():
     L.fw_multi_resolve.argtypes = [vp]
     L.fw_multi_download_local.restype = ctypes.c_int
     L.fw_multi_download_local.argtypes = [vp, i32, vp, vp]
+    L.fw_multi_download_locals.restype = ctypes.c_int
+    L.fw_multi_download_locals.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    L.fw_multi_transport.restype = ctypes.c_char_p
+    L.fw_multi_transport.argtypes = [vp]
     L.fw_multi_plan.restype = i64
     L.fw_multi_plan.argtypes = [i32, i32, i32, i32, i32, ctypes.POINTER(PlanOp), i64]
     L.fw_paths.restype = ctypes.c_int

@@ -7,6 +7,7 @@
 // not in a Python launcher.  Included at the end of fwgpu.cu (one translation unit: shares its kernels,
 // launch helpers and fw_ctx).
 #pragma once
+#include <cuda.h>    // types of the stream memory operations (entry points come from cudaGetDriverEntryPoint)
 #include <dlfcn.h>
 #include <nccl.h>   // types only; the library is dlopen'ed so that libfwgpu.so loads on boxes without NCCL
 
@@ -23,6 +24,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -47,6 +49,7 @@ int load_nccl() {
     FW_NCCL_SYM(CommDestroy, "ncclCommDestroy")
     FW_NCCL_SYM(Broadcast, "ncclBroadcast")
     FW_NCCL_SYM(AllReduce, "ncclAllReduce")
+    FW_NCCL_SYM(AllGather, "ncclAllGather")
     FW_NCCL_SYM(GroupStart, "ncclGroupStart")
     FW_NCCL_SYM(GroupEnd, "ncclGroupEnd")
     FW_NCCL_SYM(GetErrorString, "ncclGetErrorString")
@@ -120,14 +123,60 @@ struct Shard {
     DevBuf<int32_t> next, init_next, mid, csT, rs, ccy, src, dst;
     DevBuf<double> Rw[2 * fw::BULK_MAXNB];
     ncclComm_t comm = nullptr;
+    // one process per GPU, copy-engine transport: peers' panel buffers and flag words mapped through CUDA IPC
+    DevBuf<int> flags;                // [0, 16): sequence number of the last panel landed in Rw[b];  [16, 16 + world): rank t's "my buffers are free" counter
+    DevBuf<unsigned char> ipc_stage;
+    struct Peer { void *Rw[2 * fw::BULK_MAXNB]; int *flags; };
+    std::vector<Peer> peers;
 };
+
+constexpr int FLAG_ARRIVE = 0, FLAG_FREE = 2 * fw::BULK_MAXNB;
+
+// the flag words are written by a peer over NVLink after its copy has completed in stream order
+__global__ void fw_signal_kernel(int *remote, int v) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int *>(remote) = v;
+    __threadfence_system();
+}
+// fallback wait when the driver offers no stream memory operations: one thread polls a local word
+__global__ void fw_spin_wait_kernel(const int *flag, int v) {
+    while ((int)(*reinterpret_cast<const volatile int *>(flag) - v) < 0) __nanosleep(200);
+    __threadfence_system();
+}
+
+typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWaitValue32Fn g_wait_value32 = nullptr;
+bool g_wait_value32_probed = false;
+
+int stream_wait_geq(cudaStream_t st, const int *flag, int v) {
+    if (!g_wait_value32_probed) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess && !getenv("FW_MULTI_SPINWAIT"))
+            g_wait_value32 = reinterpret_cast<StreamWaitValue32Fn>(fn);
+        cudaGetLastError();
+        g_wait_value32_probed = true;
+    }
+    if (g_wait_value32) {
+        CUresult r = g_wait_value32((CUstream)st, (CUdeviceptr)(uintptr_t)flag, (cuuint32_t)v, CU_STREAM_WAIT_VALUE_GEQ);
+        if (r == CUDA_SUCCESS) return FW_OK;
+        g_wait_value32 = nullptr;       // not supported on this stream / device: poll instead
+    }
+    fw_spin_wait_kernel<<<1, 1, 0, st>>>(flag, v);
+    CU(cudaGetLastError());
+    return FW_OK;
+}
 
 }  // namespace
 
 struct fw_multi {
     int world = 1;
     bool rank_mode = false;
-    bool use_nccl = false;
+    bool use_nccl = false;            // panels by ncclBroadcast
+    bool use_ipc = false;             // one process per GPU: panels by copy-engine copies into IPC-mapped peer buffers
+    bool ipc_ready = false;
+    int bseq = 0, gseq = 0;           // sequence numbers of broadcasts / factored groups (identical on every rank)
     std::vector<Shard> sh;            // local shards (single process: all `world`; rank mode: one)
     std::recursive_mutex mu;
     std::mutex err_mu;
@@ -168,7 +217,13 @@ void shard_release(Shard &s) {
     cudaSetDevice(s.device);
     if (s.sA) cudaStreamSynchronize(s.sA);
     if (s.sB) cudaStreamSynchronize(s.sB);
+    for (auto &pr : s.peers) {
+        for (void *q : pr.Rw) if (q) cudaIpcCloseMemHandle(q);
+        if (pr.flags) cudaIpcCloseMemHandle(pr.flags);
+    }
+    s.peers.clear();
     if (s.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s.comm);
+    s.flags.release(); s.ipc_stage.release();
     s.rate.release(); s.sink.release(); s.val.release(); s.next.release(); s.init_next.release();
     s.mid.release(); s.csT.release(); s.rs.release(); s.ccy.release(); s.src.release(); s.dst.release();
     for (auto &b : s.Rw) b.release();
@@ -213,6 +268,49 @@ fwplan::Layout choose_layout(int n, int world) {
     return L;
 }
 
+// One process per GPU: every rank publishes IPC handles of its 2G panel buffers and of its flag words, gathers
+// everybody's through NCCL and maps them.  Collective; called whenever the layout (hence the buffers) changed.
+int multi_ipc_setup(fw_multi *m) {
+    Shard &s = m->sh[0];
+    const int P = m->world, NB = 2 * fw::BULK_MAXNB, nh = NB + 1;
+    const size_t hb = sizeof(cudaIpcMemHandle_t), mine = nh * hb;
+    CU(cudaSetDevice(s.device));
+    CU(cudaStreamSynchronize(s.sA));
+    CU(cudaStreamSynchronize(s.sB));
+    for (auto &pr : s.peers) {
+        for (void *&q : pr.Rw) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+        if (pr.flags) { cudaIpcCloseMemHandle(pr.flags); pr.flags = nullptr; }
+    }
+    s.peers.assign(P, Shard::Peer());
+    for (auto &pr : s.peers) { for (void *&q : pr.Rw) q = nullptr; pr.flags = nullptr; }
+    int rc;
+    if (!s.flags.p) {
+        if ((rc = s.flags.ensure(FLAG_FREE + P)) != FW_OK) return rc;
+        CU(cudaMemsetAsync(s.flags.p, 0, sizeof(int) * (FLAG_FREE + P), s.sA));
+    }
+    if ((rc = s.ipc_stage.ensure(mine * (P + 1))) != FW_OK) return rc;
+    std::vector<cudaIpcMemHandle_t> hs(nh * (size_t)(P + 1));
+    memset(hs.data(), 0, hs.size() * hb);
+    for (int b = 0; b < NB; ++b)
+        if (s.Rw[b].p) CU(cudaIpcGetMemHandle(&hs[b], s.Rw[b].p));
+    CU(cudaIpcGetMemHandle(&hs[NB], s.flags.p));
+    CU(cudaMemcpyAsync(s.ipc_stage.p, hs.data(), mine, cudaMemcpyHostToDevice, s.sA));
+    NC(g_nccl.AllGather(s.ipc_stage.p, s.ipc_stage.p + mine, mine, ncclInt8, s.comm, s.sA));
+    CU(cudaMemcpyAsync(hs.data() + nh, s.ipc_stage.p + mine, mine * P, cudaMemcpyDeviceToHost, s.sA));
+    CU(cudaStreamSynchronize(s.sA));
+    for (int t = 0; t < P; ++t) {
+        if (t == s.rank) continue;
+        const cudaIpcMemHandle_t *th = &hs[nh * (size_t)(1 + t)];
+        for (int b = 0; b < 2 * m->L.G; ++b)
+            CU(cudaIpcOpenMemHandle(&s.peers[t].Rw[b], th[b], cudaIpcMemLazyEnablePeerAccess));
+        void *fp = nullptr;
+        CU(cudaIpcOpenMemHandle(&fp, th[NB], cudaIpcMemLazyEnablePeerAccess));
+        s.peers[t].flags = static_cast<int *>(fp);
+    }
+    m->ipc_ready = true;
+    return FW_OK;
+}
+
 int multi_alloc(fw_multi *m, int n, bool want_paths) {
     if (n <= 0) return fail(FW_ERR_INVALID, "fw_multi: n must be positive");
     const fwplan::Layout L = choose_layout(n, m->world);
@@ -232,8 +330,10 @@ int multi_alloc(fw_multi *m, int n, bool want_paths) {
             if ((rc = s.ctx->Cp[set].ensure(rows * FW_B)) != FW_OK || (rc = s.ctx->NCp[set].ensure(rows * FW_B)) != FW_OK)
                 return rc;
     }
-    if (!(m->allocated && m->n == n && m->L.n == L.n && m->L.G == L.G && m->L.cbr == L.cbr)) m->coo_resident = false;
+    const bool same_layout = m->allocated && m->L.n == L.n && m->L.G == L.G && m->L.cbr == L.cbr;
+    if (!(same_layout && m->n == n)) m->coo_resident = false;
     m->n = n; m->L = L; m->want_paths = want_paths; m->allocated = true; m->solved = false;
+    if (m->use_ipc && !(same_layout && m->ipc_ready) && (rc = multi_ipc_setup(m)) != FW_OK) return rc;
     return FW_OK;
 }
 
@@ -369,6 +469,37 @@ int exec_bcast(fw_multi *m, const fw_plan_op &op) {
             NC(g_nccl.Broadcast(s.Rw[op.buf].p, s.Rw[op.buf].p, count, ncclDouble, op.rank, s.comm, s.sB));
         }
         if (m->sh.size() > 1) NC(g_nccl.GroupEnd());
+        return FW_OK;
+    }
+    if (m->use_ipc) {
+        // one process per GPU, copy engines: flag words in device memory order the ranks (no host round trips).
+        // First panel of a group: every other rank tells the owner "my buffers of this parity are free" (its
+        // look-ahead lane has waited for its main lane by then); the owner waits for all of them, pushes the
+        // panel into every peer's buffer and raises the peer's arrival word; the peers' look-ahead lanes wait on it.
+        Shard &s = m->sh[0];
+        CU(cudaSetDevice(s.device));
+        const int P = m->world;
+        const bool first = (op.buf % m->L.G) == 0;
+        if (first) ++m->gseq;
+        ++m->bseq;
+        int rc;
+        if (s.rank == op.rank) {
+            if (first)
+                for (int t = 0; t < P; ++t)
+                    if (t != s.rank && (rc = stream_wait_geq(s.sB, s.flags.p + FLAG_FREE + t, m->gseq)) != FW_OK) return rc;
+            for (int t = 0; t < P; ++t)
+                if (t != s.rank)
+                    CU(cudaMemcpyAsync(s.peers[t].Rw[op.buf], s.Rw[op.buf].p, count * 8, cudaMemcpyDeviceToDevice, s.sB));
+            for (int t = 0; t < P; ++t)
+                if (t != s.rank) fw_signal_kernel<<<1, 1, 0, s.sB>>>(s.peers[t].flags + FLAG_ARRIVE + op.buf, m->bseq);
+            CU(cudaGetLastError());
+        } else {
+            if (first) {
+                fw_signal_kernel<<<1, 1, 0, s.sB>>>(s.peers[op.rank].flags + FLAG_FREE + s.rank, m->gseq);
+                CU(cudaGetLastError());
+            }
+            if ((rc = stream_wait_geq(s.sB, s.flags.p + FLAG_ARRIVE + op.buf, m->bseq)) != FW_OK) return rc;
+        }
         return FW_OK;
     }
     // copy-engine transport (single process): the owner's look-ahead lane pushes the panel into every peer's
@@ -581,7 +712,9 @@ int multi_build(fw_multi *m) {
 int multi_common_create(fw_multi *m) {
     // transport: NCCL in rank mode; in one process copy-engine peer copies unless FW_MULTI_TRANSPORT=nccl
     const char *tr = getenv("FW_MULTI_TRANSPORT");
-    bool want_nccl = m->rank_mode ? (m->world > 1) : (tr && std::string(tr) == "nccl" && m->world > 1);
+    bool want_nccl = m->rank_mode ? (m->world > 1 && tr && std::string(tr) == "nccl")
+                                  : (tr && std::string(tr) == "nccl" && m->world > 1);
+    m->use_ipc = m->rank_mode && m->world > 1 && !want_nccl;
     if (!m->rank_mode && m->world > 1) {
         // peer access for the copies and for fw_multi_optimum's cross-shard table walk
         bool all_peers = true;
@@ -656,7 +789,7 @@ int fw_multi_create_rank(int32_t device, int32_t rank, int32_t world, const void
     m->sh.resize(1);
     int rc = shard_init(m->sh[0], device, rank);
     if (rc == FW_OK) rc = multi_common_create(m);
-    if (rc == FW_OK && m->use_nccl) {
+    if (rc == FW_OK && world > 1) {      // NCCL always bootstraps the ranks (handle exchange, agreement on validation)
         rc = load_nccl();
         if (rc == FW_OK) {
             ncclUniqueId id;
@@ -841,6 +974,28 @@ int fw_multi_optimum(fw_multi *m, int32_t src, int32_t dst, double *rate, int32_
     CU(cudaSetDevice(q.device));
     q.ctx->stream = q.sA;
     return optimum_locked(q.ctx, t, rsh, L.n, src, dst, rate, path, cap, path_len);
+}
+
+int fw_multi_download_locals(fw_multi *m, double *const *rate, int32_t *const *next) {
+    if (!m || (!rate && !next)) return fail(FW_ERR_INVALID, "fw_multi_download_locals: bad argument");
+    FW_MENTER(m);
+    if (!m->allocated) return fail(FW_ERR_INVALID, "fw_multi_download_locals: nothing allocated");
+    const size_t tot = (size_t)m->L.rows_local() * m->L.n;
+    for (size_t i = 0; i < m->sh.size(); ++i) {     // every device's two copy engines at once
+        Shard &s = m->sh[i];
+        CU(cudaSetDevice(s.device));
+        if (rate && rate[i]) CU(cudaMemcpyAsync(rate[i], s.rate.p, tot * 8, cudaMemcpyDeviceToHost, s.sA));
+        if (next && next[i]) CU(cudaMemcpyAsync(next[i], s.next.p, tot * 4, cudaMemcpyDeviceToHost, s.sB));
+    }
+    return multi_sync_all(m);
+}
+
+const char *fw_multi_transport(fw_multi *m) {
+    if (!m) return "";
+    if (m->world == 1) return "none (one shard)";
+    if (m->use_nccl) return "ncclBroadcast";
+    if (m->use_ipc) return "copy-engine copies into CUDA-IPC-mapped peer buffers, flag words + stream memory operations";
+    return "copy-engine peer copies, CUDA events";
 }
 
 int32_t fw_multi_local_shards(fw_multi *m) { return m ? (int32_t)m->sh.size() : 0; }

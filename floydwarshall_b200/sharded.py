@@ -95,6 +95,16 @@ class MultiSolver:
         self._check(self.L.fw_multi_download_local(self._h, i, ctypes.c_void_p(rate_ptr) if rate_ptr else None,
                                                    ctypes.c_void_p(next_ptr) if next_ptr else None))
 
+    def download_locals(self, rate_ptrs, next_ptrs):
+        """Every local shard into its host buffer (addresses), all devices copying at once."""
+        k = len(rate_ptrs)
+        ra = (ctypes.c_void_p * k)(*rate_ptrs)
+        xa = (ctypes.c_void_p * k)(*next_ptrs)
+        self._check(self.L.fw_multi_download_locals(self._h, ra, xa))
+
+    def transport(self) -> str:
+        return (self.L.fw_multi_transport(self._h) or b"").decode()
+
     def optimum(self, src: int, dst: int, cap: int = 4096):
         """(rate, index path) of one entry, read across the shards (Algorithms.hs:74-75)."""
         rate = ctypes.c_double()

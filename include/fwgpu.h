@@ -264,6 +264,11 @@ typedef struct fw_shard_info {
 int32_t fw_multi_local_shards(fw_multi *m);
 /* Local shard i as it lies in HBM (rows x n_padded, local row order) into host buffers; either may be NULL. */
 int fw_multi_download_local(fw_multi *m, int32_t i, double *rate, int32_t *next);
+/* All local shards at once (rate[i] / next[i] = host buffer of local shard i; arrays or entries may be NULL):
+ * the copies of all devices run concurrently. */
+int fw_multi_download_locals(fw_multi *m, double *const *rate, int32_t *const *next);
+/* How the pivot-row panels travel in this object (a static description). */
+const char *fw_multi_transport(fw_multi *m);
 int fw_multi_shard(fw_multi *m, int32_t i, fw_shard_info *out);
 /* Device time of the last solve (CUDA events, max over the local shards), kernel launches issued, and the
  * bulk kernel's share (per-launch events; only when profiling was on during the solve). */
