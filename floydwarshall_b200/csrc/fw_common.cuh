@@ -50,6 +50,23 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// shared-memory mbarriers (split arrive / wait: the tile kernel lets warps run one step ahead of each other)
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n .reg .pred p;\n"
+        "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @!p bra W;\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+
 // Swizzled position of column `col` (0..127) inside a 128-wide shared row so
 // that a thread owning 8 consecutive columns [l*8, l*8+8) reads them as four
 // conflict-free LDS.128: position = q*32 + l*2 + e  for col = l*8 + q*2 + e.

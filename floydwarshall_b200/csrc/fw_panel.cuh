@@ -58,7 +58,7 @@ __device__ __forceinline__ int and8(const int (&h)[8]) {
 }
 
 template <bool PATHS, int NJ>
-__global__ void __launch_bounds__(512, 1) fw_colpanel_kernel(PanelArgs a) {
+__device__ __forceinline__ void colpanel_body(const PanelArgs &a, const int bid, const int nctas) {
     constexpr int PANEL_JOBS = 32 * NJ;   // jobs per CTA pass
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *Fs = reinterpret_cast<double *>(smem_raw);
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(512, 1) fw_colpanel_kernel(PanelArgs a) {
 
     const int job = tid >> 4, l = tid & 15;
     const int nrows = a.rows - (a.skip_r0 < a.rows ? a.skipn : 0);
-    for (int g = blockIdx.x; g * PANEL_JOBS < nrows; g += gridDim.x) {
+    for (int g = bid; g * PANEL_JOBS < nrows; g += nctas) {
         long long off[NJ];
         int irow[NJ];
         double y[NJ][8];
@@ -167,7 +167,12 @@ __global__ void __launch_bounds__(512, 1) fw_colpanel_kernel(PanelArgs a) {
 }
 
 template <bool PATHS, int NJ>
-__global__ void __launch_bounds__(512, 1) fw_rowpanel_kernel(PanelArgs a) {
+__global__ void __launch_bounds__(512, 1) fw_colpanel_kernel(PanelArgs a) {
+    colpanel_body<PATHS, NJ>(a, (int)blockIdx.x, (int)gridDim.x);
+}
+
+template <bool PATHS, int NJ>
+__device__ __forceinline__ void rowpanel_body(const PanelArgs &a, const int bid, const int nctas) {
     constexpr int PANEL_JOBS = 32 * NJ;   // jobs per CTA pass
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *Fs = reinterpret_cast<double *>(smem_raw);
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(512, 1) fw_rowpanel_kernel(PanelArgs a) {
 
     const int job = tid >> 4, l = tid & 15;
     const int ncols = a.npad - FW_B;
-    for (int g = blockIdx.x; g * PANEL_JOBS < ncols; g += gridDim.x) {
+    for (int g = bid; g * PANEL_JOBS < ncols; g += nctas) {
         // NJ adjacent columns per half-warp (never straddling the k-block: b0 and NJ divide 128)
         const int jp = g * PANEL_JOBS + job * NJ;
         const int j = jp < b0 ? jp : jp + FW_B;
@@ -253,6 +258,20 @@ __global__ void __launch_bounds__(512, 1) fw_rowpanel_kernel(PanelArgs a) {
                 }
             }
     }
+}
+
+template <bool PATHS, int NJ>
+__global__ void __launch_bounds__(512, 1) fw_rowpanel_kernel(PanelArgs a) {
+    rowpanel_body<PATHS, NJ>(a, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// Both panels of a k-block in ONE launch: they depend only on the diagonal tile's snapshots and write disjoint
+// strips, so the first col_ctas CTAs take the column panel and the others the row panel.  At small N (a panel
+// fills a fraction of the SMs) the two then run side by side instead of one after the other.
+template <bool PATHS, int NJ>
+__global__ void __launch_bounds__(512, 1) fw_panels_kernel(PanelArgs a, int col_ctas) {
+    if ((int)blockIdx.x < col_ctas) colpanel_body<PATHS, NJ>(a, (int)blockIdx.x, col_ctas);
+    else rowpanel_body<PATHS, NJ>(a, (int)blockIdx.x - col_ctas, (int)gridDim.x - col_ctas);
 }
 
 }  // namespace fw

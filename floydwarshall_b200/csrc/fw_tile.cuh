@@ -17,7 +17,15 @@
 // vectors; everybody else reads 4 + 8 operands and runs a 4x8 micro-tile of
 // mul / compare / select.  next-hops (and mids) live in shared memory and are
 // written with predicated stores only when a relaxation fires (1-2 % of them).
-// One __syncthreads per step.
+//
+// Step-to-step synchronisation (FW_TILE_PIPE): a full barrier per step left the SM idle for a third of the
+// time (ncu: barrier stalls 0.48 per issue at 49 % issue activity, profiles/r01d_pivot_phases_ncu_summary.json).
+// Every thread now relaxes FIRST the entries of its micro-tile that lie in row k+1 / column k+1 (the entries
+// of a step are independent, so their order is free), the owners publish them, and the warp ARRIVES on the
+// mbarrier that guards step k+1 before it relaxes the other 21 entries.  A warp that starts step k+1 waits
+// only for those arrivals, i.e. for the next operands -- not for the slowest warp's whole step.  Warps are
+// never more than one step apart, which is what the double-buffered row / column vectors allow; column k+1
+// and row k+1 of next / mid are final before the arrival as well, so the snapshot reads stay exact.
 #pragma once
 #include "fw_common.cuh"
 
@@ -42,8 +50,11 @@ struct TileArgs {
 };
 
 constexpr int TILE_NXP = 132;  // padded pitch of the shared next/mid tiles (ints)
+#ifndef FW_TILE_PIPE
+#define FW_TILE_PIPE 1   // 1: warps run up to one step ahead of each other (mbarrier arrive / wait); 0: one __syncthreads per step
+#endif
 constexpr size_t tile_smem_bytes(bool paths) {
-    return (size_t)(paths ? 2 : 1) * 128 * TILE_NXP * 4 + 4 * 128 * 8;
+    return (size_t)(paths ? 2 : 1) * 128 * TILE_NXP * 4 + 4 * 128 * 8 + 16;
 }
 
 template <bool PATHS>
@@ -92,6 +103,16 @@ __global__ void __launch_bounds__(512, 1) fw_tile_kernel(TileArgs a) {
 
     int32_t *nxp = NXs + (ty * 4) * TILE_NXP + tx * 8;
     int32_t *mdp = MIDs + (ty * 4) * TILE_NXP + tx * 8;
+#if FW_TILE_PIPE
+    // bars[b] guards the operands of the steps k = b (mod 2), k >= 1; 16 warps arrive once per use
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(rowbuf + 256);
+    if (tid == 0) {
+        mbar_init(bar0, 16);
+        mbar_init(bar0 + 8, 16);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();     // tile loaded, column 0 / row 0 published, barriers ready
+#endif
 
     for (int kt = 0; kt < 16; ++kt) {
         if (kt * 8 >= nv) break;
@@ -99,7 +120,11 @@ __global__ void __launch_bounds__(512, 1) fw_tile_kernel(TileArgs a) {
         for (int c = 0; c < 8; ++c) {
             const int k = kt * 8 + c;
             const int buf = c & 1;
+#if FW_TILE_PIPE
+            if (k >= 1 && k < nv) mbar_wait(bar0 + 8 * buf, ((k - 1) >> 1) & 1);   // row k / column k are published
+#else
             __syncthreads();
+#endif
             if (k < nv) {  // uniform
                 const double *cb = colbuf + buf * 128;
                 const double *rb = rowbuf + buf * 128;
@@ -142,27 +167,36 @@ __global__ void __launch_bounds__(512, 1) fw_tile_kernel(TileArgs a) {
                     }
                 }
                 const int kabs = a.b0 + k;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                    for (int cc = 0; cc < 8; ++cc) {
-                        const double n = av[r] * bv[cc];
-                        if (o[r][cc] < n) {
-                            o[r][cc] = n;
-                            nxp[r * TILE_NXP + cc] = an[r];
-                            if (PATHS) mdp[r * TILE_NXP + cc] = kabs;
-                        }
+                auto relax1 = [&](int r, int cc) {
+                    const double n = av[r] * bv[cc];          // one rounded multiply (Algorithms.hs:61)
+                    if (o[r][cc] < n) {                       // strict (Algorithms.hs:55)
+                        o[r][cc] = n;
+                        nxp[r * TILE_NXP + cc] = an[r];
+                        if (PATHS) mdp[r * TILE_NXP + cc] = kabs;
                     }
-                }
+                };
+                const int cn = (c + 1) & 7;       // micro-tile column that holds matrix column k+1 (for tx == ktn)
+                const int rn = (c + 1) & 3;       // micro-tile row that holds matrix row k+1 (for ty == tyn)
+#if FW_TILE_PIPE
+                // the entries next step's operands come from go first ...
+#pragma unroll
+                for (int r = 0; r < 4; ++r) relax1(r, cn);
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                    if (cc != cn) relax1(rn, cc);
+#else
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc) relax1(r, cc);
+#endif
                 // publish column k+1 / row k+1 (values after step k) into the other buffer
-                const int cn = (c + 1) & 7;
                 const int ktn = kt + ((c == 7) ? 1 : 0);
                 if (tx == ktn) {
                     double *cbn = colbuf + (buf ^ 1) * 128 + ty * 4;
                     *reinterpret_cast<double2 *>(cbn) = make_double2(o[0][cn], o[1][cn]);
                     *reinterpret_cast<double2 *>(cbn + 2) = make_double2(o[2][cn], o[3][cn]);
                 }
-                const int rn = (c + 1) & 3;
                 const int tyn = kt * 2 + ((c + 1) >> 2);
                 if (ty == tyn) {
                     double *rbn = rowbuf + (buf ^ 1) * 128;
@@ -171,6 +205,16 @@ __global__ void __launch_bounds__(512, 1) fw_tile_kernel(TileArgs a) {
                         *reinterpret_cast<double2 *>(rbn + q * 32 + tx * 2) =
                             make_double2(o[rn][q * 2], o[rn][q * 2 + 1]);
                 }
+#if FW_TILE_PIPE
+                // ... then the warp arrives for step k+1 and relaxes the rest
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(bar0 + 8 * (buf ^ 1));
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int cc = 0; cc < 8; ++cc)
+                        if (r != rn && cc != cn) relax1(r, cc);
+#endif
             }
         }
     }

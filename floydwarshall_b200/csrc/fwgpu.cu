@@ -202,6 +202,7 @@ struct fw_ctx {
     int fuse_group = 0;            // k-blocks per fused bulk launch, 0 = by size: knob FW_FUSE_GROUP=1|2|4|8 (forces it for every
     bool fuse_forced = false;      // size); FW_FUSE_PAIRS=0 / =2 kept as aliases of FW_FUSE_GROUP=1 / =2
     int panel_nj = 0;              // knob FW_PANEL_NJ=1|2 forces the jobs per half-warp of the panel kernels (0: by size)
+    bool merge_panels = true;      // knob FW_MERGE_PANELS=0: column and row panel as two launches
     // padded working copy (n not a multiple of FW_B) and host-API staging
     DevBuf<double> w_rate;
     DevBuf<int32_t> w_next, w_mid, w_csT, w_rs;
@@ -268,6 +269,11 @@ int set_kernel_attrs(fw_ctx *c) {
         if (v == 1 || v == 2 || v == 4 || v == 8) { c->fuse_group = v; c->fuse_forced = true; }
     }
     if (const char *e = getenv("FW_PANEL_NJ")) c->panel_nj = atoi(e);
+    if (const char *e = getenv("FW_MERGE_PANELS")) c->merge_panels = atoi(e) != 0;
+    CU(cudaFuncSetAttribute(fw::fw_panels_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw::panel_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_panels_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw::panel_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_panels_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw::panel_smem_bytes()));
+    CU(cudaFuncSetAttribute(fw::fw_panels_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fw::panel_smem_bytes()));
     if (const char *e = getenv("FW_BULK_BAND")) c->bulk_band = atoi(e) > 0 ? atoi(e) : 64;
     c->attrs_set = true;
     return FW_OK;
@@ -340,6 +346,17 @@ void launch_panel(fw_ctx *c, const fw::PanelArgs &p, int jobs, bool paths, cudaS
 }
 
 
+// Column and row panel of one k-block in one launch (both have `jobs` jobs).
+void launch_both_panels(fw_ctx *c, const fw::PanelArgs &p, int jobs, bool paths, cudaStream_t st) {
+    const int nj = (c->panel_nj == 1 || c->panel_nj == 2) ? c->panel_nj : fw::panel_nj(jobs, c->sm_count);
+    const int passes = jobs / (32 * nj);
+    const int each = passes < c->sm_count ? passes : c->sm_count;
+    const size_t sm = fw::panel_smem_bytes();
+    if (paths) { if (nj == 2) fw::fw_panels_kernel<true, 2><<<2 * each, 512, sm, st>>>(p, each); else fw::fw_panels_kernel<true, 1><<<2 * each, 512, sm, st>>>(p, each); }
+    else       { if (nj == 2) fw::fw_panels_kernel<false, 2><<<2 * each, 512, sm, st>>>(p, each); else fw::fw_panels_kernel<false, 1><<<2 * each, 512, sm, st>>>(p, each); }
+    c->launches++;
+}
+
 // Domain check (synchronises the stream once).
 int validate_device(fw_ctx *c, const double *rate, const int32_t *next, long long ld, long long stride,
                     int batch, int n, int rows = -1, int cbr = 1 << 30, int P = 1, int r = 0, int nvalid = -1,
@@ -381,13 +398,18 @@ int launch_pivot_phases(fw_ctx *c, int npad, long long ld, double *rate, int32_t
         p.rate = rate; p.next = next; p.mid = mid; p.csT = csT; p.rs = rs;
         p.ld = ld; p.npad = npad; p.b0 = b0; p.rows = npad; p.blk_r0 = b0; p.skip_r0 = b0; p.skipn = FW_B;
         p.Cp = c->Cp[set].p; p.ldc = npad; p.NCp = c->NCp[set].p; p.Rw = c->Rw[set].p; p.ldw = npad;
-        {
-            PhaseTimer pt(c, 1);
-            launch_panel<true>(c, p, npad - FW_B, paths, (c->cur ? c->cur : c->stream));
-        }
-        {
-            PhaseTimer pt(c, 2);
-            launch_panel<false>(c, p, npad - FW_B, paths, (c->cur ? c->cur : c->stream));
+        if (c->merge_panels) {
+            PhaseTimer pt(c, 1);          // column + row panel, one launch (reported under "col_panel")
+            launch_both_panels(c, p, npad - FW_B, paths, (c->cur ? c->cur : c->stream));
+        } else {
+            {
+                PhaseTimer pt(c, 1);
+                launch_panel<true>(c, p, npad - FW_B, paths, (c->cur ? c->cur : c->stream));
+            }
+            {
+                PhaseTimer pt(c, 2);
+                launch_panel<false>(c, p, npad - FW_B, paths, (c->cur ? c->cur : c->stream));
+            }
         }
     }
     CU(cudaGetLastError());

@@ -15,7 +15,8 @@
 -- (floydwarshall_b200/algorithms.py + tests/).  See INTEGRATION.md for the cabal changes.
 module FwGpu
   ( floydWarshallGpu
-  , fwLastError
+  , floydWarshallMultiGpu
+  , fwCtxLastError
   ) where
 
 import Protolude
@@ -42,11 +43,43 @@ foreign import ccall safe "fw_solve_edges"
                    -> Ptr CDouble -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32
                    -> IO CInt
 
-foreign import ccall unsafe "fw_last_error"
-  c_fw_last_error :: IO (Ptr CChar)
+-- const char* fw_ctx_last_error(fw_ctx*);  NULL = the default context.
+-- The text is kept PER CONTEXT, not per OS thread: a `safe` call and the query after it may run on
+-- different OS threads for an unbound Haskell thread, so the thread-local fw_last_error() is not used here.
+foreign import ccall unsafe "fw_ctx_last_error"
+  c_fw_ctx_last_error :: Ptr () -> IO (Ptr CChar)
 
-fwLastError :: IO Text
-fwLastError = toS <$> (c_fw_last_error >>= peekCString)
+fwCtxLastError :: Ptr () -> IO Text
+fwCtxLastError ctx = toS <$> (c_fw_ctx_last_error ctx >>= peekCString)
+
+-- The multi-GPU object (include/fwgpu.h, "multi-GPU solve"): one process drives every GPU of the box.
+--   int fw_multi_create(int32_t ndev, const int32_t* devices, fw_multi** out);
+--   int fw_multi_solve_edges(fw_multi*, int32_t n, const int32_t* ccy, int32_t m, const int32_t* src,
+--                            const int32_t* dst, const double* val, double* rate, int32_t* next,
+--                            int32_t* init_next, int32_t* mid, int32_t* csT, int32_t* rs);
+--   const char* fw_multi_last_error(fw_multi*);
+-- For the REPL flow bind fw_multi_sync (on OutSync) + fw_multi_optimum (per request) instead: the optimised
+-- matrix then stays sharded in HBM and only the requested entry and its path cross PCIe.
+foreign import ccall safe "fw_multi_create"
+  c_fw_multi_create :: Int32 -> Ptr Int32 -> Ptr (Ptr ()) -> IO CInt
+foreign import ccall safe "fw_multi_solve_edges"
+  c_fw_multi_solve_edges :: Ptr () -> Int32 -> Ptr Int32 -> Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr CDouble
+                         -> Ptr CDouble -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32
+                         -> IO CInt
+foreign import ccall unsafe "fw_multi_last_error"
+  c_fw_multi_last_error :: Ptr () -> IO (Ptr CChar)
+foreign import ccall unsafe "fw_device_count"
+  c_fw_device_count :: IO CInt
+
+-- | One fw_multi object over all GPUs of the box, created on first use and kept for the process.
+multiHandle :: Ptr ()
+multiHandle = unsafePerformIO $ do
+  ndev <- c_fw_device_count
+  alloca $ \out -> do
+    rc <- c_fw_multi_create (fromIntegral ndev) nullPtr out
+    when (rc /= 0) $ throwIO (userError ("fw_multi_create failed (" <> show rc <> ")"))
+    peek out
+{-# NOINLINE multiHandle #-}
 
 -- | The five dense n x n tables of a solve (row-major).
 data Solved = Solved
@@ -62,7 +95,7 @@ floydWarshallGpu :: M.Map (Vertex, Vertex) Double -> Matrix RateEntry
 floydWarshallGpu exRates
   | V.null vertices = V.empty                                -- AlgorithmsTest.hs:62-64
   | otherwise = unsafePerformIO $ do                         -- pure caller: ProcessRequests.hs:82-84
-      solved <- solveEdges n ccyIds edges
+      solved <- solveEdges (c_fw_solve_edges nullPtr) (fwCtxLastError nullPtr) n ccyIds edges
       pure $ V.generate n $ \i -> V.generate n $ \j ->
         RateEntry { _bestRate = realToFrac (sRate solved S.! (i * n + j))
                   , _start    = vertices V.! i
@@ -80,8 +113,32 @@ floydWarshallGpu exRates
     edges    = [(ix a, ix b, r) | ((a, b), r) <- M.toList exRates]
 {-# NOINLINE floydWarshallGpu #-}
 
-solveEdges :: Int -> S.Vector Int32 -> [(Int32, Int32, Double)] -> IO Solved
-solveEdges n ccyIds edges = do
+-- | The same function on every GPU of the box (rows sharded over the GPUs, pivot-row panels over NVLink).
+floydWarshallMultiGpu :: M.Map (Vertex, Vertex) Double -> Matrix RateEntry
+floydWarshallMultiGpu exRates
+  | V.null vertices = V.empty
+  | otherwise = unsafePerformIO $ do
+      solved <- solveEdges (c_fw_multi_solve_edges multiHandle)
+                           (toS <$> (c_fw_multi_last_error multiHandle >>= peekCString)) n ccyIds edges
+      pure $ V.generate n $ \i -> V.generate n $ \j ->
+        RateEntry { _bestRate = realToFrac (sRate solved S.! (i * n + j))
+                  , _start    = vertices V.! i
+                  , _path     = map (vertices V.!) (pathOf n solved i j) }
+  where
+    vertices = V.fromList . L.sort . L.nub $ M.keys exRates >>= \(a, b) -> [a, b]
+    n        = V.length vertices
+    index    = M.fromList (zip (V.toList vertices) [0 ..]) :: M.Map Vertex Int
+    ix v     = fromIntegral (index M.! v) :: Int32
+    ccyTable = M.fromList (zip (L.nub (map _ccy (V.toList vertices))) [0 ..]) :: M.Map Text Int32
+    ccyIds   = S.fromList [ccyTable M.! _ccy v | v <- V.toList vertices]
+    edges    = [(ix a, ix b, r) | ((a, b), r) <- M.toList exRates]
+{-# NOINLINE floydWarshallMultiGpu #-}
+
+type SolveEdgesCall = Int32 -> Ptr Int32 -> Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr CDouble
+                    -> Ptr CDouble -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> Ptr Int32 -> IO CInt
+
+solveEdges :: SolveEdgesCall -> IO Text -> Int -> S.Vector Int32 -> [(Int32, Int32, Double)] -> IO Solved
+solveEdges call lastError n ccyIds edges = do
   let m    = length edges
       srcV = S.fromList [a | (a, _, _) <- edges]
       dstV = S.fromList [b | (_, b, _) <- edges]
@@ -96,9 +153,9 @@ solveEdges n ccyIds edges = do
         S.unsafeWith valV $ \pv -> SM.unsafeWith rate $ \pr -> SM.unsafeWith next $ \pn ->
         SM.unsafeWith ini $ \pi' -> SM.unsafeWith mid $ \pm -> SM.unsafeWith csT $ \pcs ->
         SM.unsafeWith rs $ \prs ->
-          c_fw_solve_edges nullPtr (fromIntegral n) pc (fromIntegral m) ps pd pv pr pn pi' pm pcs prs
+          call (fromIntegral n) pc (fromIntegral m) ps pd pv pr pn pi' pm pcs prs
   when (rc /= 0) $ do
-    msg <- fwLastError
+    msg <- lastError
     -- no CPU fallback: the REPL keeps its previous state on an exception (src/app/Main.hs:30-33)
     throwIO (userError ("fwgpu (" <> show rc <> "): " <> toS msg))
   Solved <$> S.unsafeFreeze rate <*> S.unsafeFreeze ini <*> S.unsafeFreeze mid
