@@ -78,6 +78,9 @@ constexpr int BULK_UNROLL = FW_BULK_UNROLL;
 #ifndef FW_BULK_TMA
 #define FW_BULK_TMA 0          // 1: panels staged by cp.async.bulk (TMA, 1-D) + mbarriers instead of cp.async (LDGSTS)
 #endif
+#ifndef FW_BULK_ONELEVEL
+#define FW_BULK_ONELEVEL 0     // 1: one flat AND tree over the 32 sign words of a step; the per-row words the replay selects rows by are recomputed on the (rare) exact path
+#endif
 #ifndef FW_BULK_LATEVOTE
 #define FW_BULK_LATEVOTE 0     // 1: vote on step k's sign words after step k+1's DFMAs (loop_probe V7: +5 % in isolation, -3.5 % in the solve)
 #endif
@@ -284,6 +287,32 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
         };
         // exact path for step `ks` of this chunk (operands re-read from shared memory: it is rare):
         // one rounded multiply, strict compare (Algorithms.hs:55,61), rows selected by their sign words
+#if FW_BULK_ONELEVEL
+        auto vote_and_replay_flat = [&](const int acc, int ks) {
+            if (__builtin_expect(__any_sync(0xffffffffu, acc >= 0), 0)) {
+                const int kloc = ch * BULK_KC + ks;
+                double ax[8], bx[NC];
+                fetch(ks, ax, bx);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    int h[NC];
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) h[c] = __double2hiint(__fma_rd(ax[r], bx[c], -o[r][c]));
+                    if (__any_sync(0xffffffffu, and_tree<NC>(h) >= 0)) {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            const double n = ax[r] * bx[c];
+                            if (o[r][c] < n) {
+                                o[r][c] = n;
+                                Ms[r * NC + c][tid] = kloc;
+                                chg |= 1ull << (r * NC + c);
+                            }
+                        }
+                    }
+                }
+            }
+        };
+#endif
         auto vote_and_replay = [&](const int (&rw)[8], int ks) {
             const int acc = and_tree<8>(rw);
 #ifdef FW_BULK_STATS
@@ -340,6 +369,9 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
             for (int r = 0; r < 8; ++r)
 #pragma unroll
                 for (int c = 0; c < NC; ++c) hi[r][c] = __double2hiint(__fma_rd(av[r], bv[c], -o[r][c]));
+#if FW_BULK_ONELEVEL
+            vote_and_replay_flat(and_tree<8 * NC>(&hi[0][0]), kk);
+#else
             // two levels: accr[r] covers micro-tile row r, acc the whole step
             int accr[8];
 #pragma unroll
@@ -354,6 +386,7 @@ __global__ void __launch_bounds__(128, (CQ == 2 ? FW_BULK_MINCTAS : 2)) fw_bulk_
             for (int r = 0; r < 8; ++r) hprev[r] = accr[r];
 #else
             vote_and_replay(accr, kk);
+#endif
 #endif
 #if FW_BULK_PREFETCH
 #pragma unroll

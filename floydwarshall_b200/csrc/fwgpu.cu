@@ -195,6 +195,10 @@ struct fw_ctx {
     std::recursive_mutex mu;
     std::mutex err_mu;
     std::string err, err_ret;      // text of the last failure on this context (fw_ctx_last_error)
+    // Lifetime: fw_state / fw_tables objects keep a reference, so a context destroyed before them (a garbage
+    // collector may finalise the objects in any order) stays allocated as a closed shell until the last goes.
+    std::atomic<int> refs{1};
+    bool closed = false;
     int64_t launches = 0;
     // snapshot panels
     DevBuf<double> Cp[16], Rw[16];   // panel sets: k-blocks go in groups of up to 8, and the next group is factored ahead
@@ -697,22 +701,33 @@ int fw_ctx_create(int device, fw_ctx **out) {
     return FW_OK;
 }
 
+static void ctx_unref(fw_ctx *c) {
+    if (c->refs.fetch_sub(1) == 1) delete c;
+}
+
 void fw_ctx_destroy(fw_ctx *c) {
     if (!c) return;
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    if (c->edge_state) { fw_state_destroy(c->edge_state); c->edge_state = nullptr; }
-    if (c->pscratch) { c->pscratch->release(); delete c->pscratch; c->pscratch = nullptr; }
-    for (int i = 0; i < 16; ++i) { c->Cp[i].release(); c->Rw[i].release(); c->NCp[i].release(); }
-    c->w_rate.release(); c->w_next.release(); c->w_mid.release(); c->w_csT.release(); c->w_rs.release();
-    c->s_rate.release(); c->s_next.release(); c->s_mid.release(); c->s_csT.release(); c->s_rs.release();
-    if (c->d_flag) cudaFree(c->d_flag);
-    if (c->h_flag) cudaFreeHost(c->h_flag);
-    if (c->own_stream) cudaStreamDestroy(c->own_stream);
-    if (c->side_stream) cudaStreamDestroy(c->side_stream);
-    if (c->ev_main) cudaEventDestroy(c->ev_main);
-    if (c->ev_side) cudaEventDestroy(c->ev_side);
-    delete c;
+    {
+        std::lock_guard<std::recursive_mutex> lk(c->mu);
+        if (c->closed) return;
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        if (c->edge_state) { fw_state_destroy(c->edge_state); c->edge_state = nullptr; }
+        if (c->pscratch) { c->pscratch->release(); delete c->pscratch; c->pscratch = nullptr; }
+        for (int i = 0; i < 16; ++i) { c->Cp[i].release(); c->Rw[i].release(); c->NCp[i].release(); }
+        c->w_rate.release(); c->w_next.release(); c->w_mid.release(); c->w_csT.release(); c->w_rs.release();
+        c->s_rate.release(); c->s_next.release(); c->s_mid.release(); c->s_csT.release(); c->s_rs.release();
+        if (c->d_flag) cudaFree(c->d_flag);
+        if (c->h_flag) cudaFreeHost(c->h_flag);
+        if (c->own_stream) cudaStreamDestroy(c->own_stream);
+        if (c->side_stream) cudaStreamDestroy(c->side_stream);
+        if (c->ev_main) cudaEventDestroy(c->ev_main);
+        if (c->ev_side) cudaEventDestroy(c->ev_side);
+        c->d_flag = nullptr; c->h_flag = nullptr; c->own_stream = c->side_stream = c->stream = nullptr;
+        c->ev_main = c->ev_side = nullptr;
+        c->closed = true;
+    }
+    ctx_unref(c);
 }
 
 int fw_ctx_set_stream(fw_ctx *c, void *cuda_stream, int external) {
@@ -1119,6 +1134,7 @@ int fw_tables_create(fw_ctx *c, int32_t n, const int32_t *init_next, const int32
     if (rc != FW_OK) return rc;
     FW_ENTER(c);
     CU(cudaSetDevice(c->device));
+    if (c->closed) return fail(FW_ERR_INVALID, "fw_tables_create: the context has been destroyed");
     fw_tables *t = new (std::nothrow) fw_tables();
     if (!t) return fail(FW_ERR_NOMEM, "out of host memory");
     t->ctx = c; t->n = n;
@@ -1133,21 +1149,27 @@ int fw_tables_create(fw_ctx *c, int32_t n, const int32_t *init_next, const int32
     }
     cudaError_t e = cudaStreamSynchronize(c->stream);   // the host tables may be freed by the caller after this returns
     if (e != cudaSuccess) { for (int j = 0; j < 4; ++j) t->t[j].release(); delete t; return cuda_fail(e, "fw_tables_create"); }
+    c->refs.fetch_add(1);
     *out = t;
     return FW_OK;
 }
 
 void fw_tables_destroy(fw_tables *t) {
     if (!t) return;
-    FW_ENTER(t->ctx);
-    cudaSetDevice(t->ctx->device);
-    cudaStreamSynchronize(t->ctx->stream);
-    for (int j = 0; j < 4; ++j) t->t[j].release();
-    delete t;
+    fw_ctx *c = t->ctx;
+    {
+        FW_ENTER(c);
+        cudaSetDevice(c->device);
+        if (!c->closed) cudaStreamSynchronize(c->stream);
+        for (int j = 0; j < 4; ++j) t->t[j].release();
+        delete t;
+    }
+    ctx_unref(c);
 }
 
 int fw_tables_paths(fw_tables *t, int32_t nq, const int32_t *queries, int64_t *offsets, int32_t *verts, int64_t cap) {
     if (!t || nq < 0 || !offsets) return fail(FW_ERR_INVALID, "fw_tables_paths: bad argument");
+    if (t->ctx->closed) return fail(FW_ERR_INVALID, "fw_tables_paths: the context of these tables has been destroyed");
     return fw_paths_device(t->ctx, t->n, t->n, t->t[0].p, t->t[1].p, t->t[2].p, t->t[3].p, nq, queries, offsets, verts, cap);
 }
 
@@ -1231,20 +1253,27 @@ int fw_state_create(fw_ctx *c, fw_state **out) {
     *out = nullptr;
     int rc = get_ctx(c, &c);
     if (rc != FW_OK) return rc;
+    if (c->closed) return fail(FW_ERR_INVALID, "fw_state_create: the context has been destroyed");
     fw_state *s = new (std::nothrow) fw_state();
     if (!s) return fail(FW_ERR_NOMEM, "out of host memory");
     s->ctx = c;
+    c->refs.fetch_add(1);
     *out = s;
     return FW_OK;
 }
 
 void fw_state_destroy(fw_state *s) {
     if (!s) return;
-    cudaSetDevice(s->ctx->device);
-    cudaStreamSynchronize(s->ctx->stream);
-    s->rate.release(); s->next.release(); s->init_next.release(); s->mid.release(); s->csT.release();
-    s->rs.release(); s->ccy.release(); s->src.release(); s->dst.release(); s->val.release();
-    delete s;
+    fw_ctx *c = s->ctx;
+    {
+        FW_ENTER(c);
+        cudaSetDevice(c->device);
+        if (!c->closed) cudaStreamSynchronize(c->stream);
+        s->rate.release(); s->next.release(); s->init_next.release(); s->mid.release(); s->csT.release();
+        s->rs.release(); s->ccy.release(); s->src.release(); s->dst.release(); s->val.release();
+        delete s;
+    }
+    ctx_unref(c);
 }
 
 int fw_state_sync(fw_state *s, int32_t n, const int32_t *ccy, int32_t m, const int32_t *src, const int32_t *dst,
@@ -1252,6 +1281,7 @@ int fw_state_sync(fw_state *s, int32_t n, const int32_t *ccy, int32_t m, const i
     if (!s || n < 0 || m < 0) return fail(FW_ERR_INVALID, "fw_state_sync: bad argument");
     fw_ctx *c = s->ctx;
     FW_ENTER(c);
+    if (c->closed) return fail(FW_ERR_INVALID, "fw_state_sync: the context of this state has been destroyed");
     CU(cudaSetDevice(c->device));
     c->launches = 0;
     recycle_spans(c);
@@ -1295,6 +1325,7 @@ int fw_state_optimum(fw_state *s, int32_t src, int32_t dst, double *rate, int32_
         return fail(FW_ERR_INVALID, "fw_state_optimum: bad argument");
     fw_ctx *c = s->ctx;
     FW_ENTER(c);
+    if (c->closed) return fail(FW_ERR_INVALID, "fw_state_optimum: the context of this state has been destroyed");
     if (!s->synced) return fail(FW_ERR_INVALID, "fw_state_optimum: state is not in sync (call fw_state_sync)");
     if (!s->want_paths) return fail(FW_ERR_INVALID, "fw_state_optimum: state was synced without path tables");
     if (src < 0 || dst < 0 || src >= s->n || dst >= s->n) return fail(FW_ERR_INVALID, "fw_state_optimum: vertex index out of range");
@@ -1306,7 +1337,7 @@ int fw_state_optimum(fw_state *s, int32_t src, int32_t dst, double *rate, int32_
 }
 
 int fw_state_download(fw_state *s, double *rate, int32_t *next) {
-    if (!s || !s->synced) return fail(FW_ERR_INVALID, "fw_state_download: state is not in sync");
+    if (!s || !s->synced || s->ctx->closed) return fail(FW_ERR_INVALID, "fw_state_download: state is not in sync");
     if (s->n == 0) return FW_OK;
     fw_ctx *c = s->ctx;
     FW_ENTER(c);

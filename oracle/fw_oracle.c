@@ -41,6 +41,18 @@ static void omp_set_num_threads(int n) { (void)n; }
 #endif
 #endif
 
+/* threads > 0: that many OpenMP threads; threads <= 0: every core of the host.  (The setting is sticky in
+ * OpenMP, so "all cores" has to be requested explicitly -- an earlier single-threaded call would otherwise
+ * leave every later call single-threaded.) */
+static void fw_oracle_set_threads(int32_t threads)
+{
+#ifdef _OPENMP
+    omp_set_num_threads(threads > 0 ? threads : omp_get_num_procs());
+#else
+    (void)threads;
+#endif
+}
+
 /*
  * fw_oracle_run_generations -- the literal form.
  *
@@ -139,11 +151,7 @@ int64_t fw_oracle_run_inplace(int32_t n, double *rate, int32_t *next,
     if (n <= 0) return 0;
     size_t nn = (size_t)n * (size_t)n;
     if (mid) for (size_t e = 0; e < nn; ++e) mid[e] = -1;
-#ifdef _OPENMP
-    if (threads > 0) omp_set_num_threads(threads);
-#else
-    (void)threads;
-#endif
+    fw_oracle_set_threads(threads);
     int64_t updates = 0;
     for (int32_t k = 0; k < n; ++k) {
         if (mid && csT) for (int32_t i = 0; i < n; ++i) csT[(size_t)i * n + k] = mid[(size_t)i * n + k];
@@ -182,11 +190,7 @@ int64_t fw_oracle_run_ksteps(int32_t n, double *rate, int32_t *next,
                              int32_t k0, int32_t k1, int32_t threads)
 {
     if (n <= 0) return 0;
-#ifdef _OPENMP
-    if (threads > 0) omp_set_num_threads(threads);
-#else
-    (void)threads;
-#endif
+    fw_oracle_set_threads(threads);
     int64_t updates = 0;
     if (k1 > n) k1 = n;
     for (int32_t k = k0; k < k1; ++k) {
@@ -223,11 +227,7 @@ int64_t fw_oracle_run_batched(int32_t batch, int32_t n, double *rate, int32_t *n
                               int32_t *mid, int32_t *csT, int32_t *rs, int32_t threads)
 {
     if (n <= 0 || batch <= 0) return 0;
-#ifdef _OPENMP
-    if (threads > 0) omp_set_num_threads(threads);
-#else
-    (void)threads;
-#endif
+    fw_oracle_set_threads(threads);
     const size_t nn = (size_t)n * (size_t)n;
     int64_t updates = 0;
 #pragma omp parallel for schedule(dynamic, 4) reduction(+ : updates)
@@ -290,11 +290,7 @@ int64_t fw_oracle_replay_rows(int32_t n, int32_t nrows, const int32_t *rows, con
                               int32_t *mid_at_i, int32_t threads)
 {
     if (n <= 0 || nrows <= 0) return 0;
-#ifdef _OPENMP
-    if (threads > 0) omp_set_num_threads(threads);
-#else
-    (void)threads;
-#endif
+    fw_oracle_set_threads(threads);
     int64_t updates = 0;
     int32_t bad = -1;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : updates)
