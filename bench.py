@@ -593,6 +593,9 @@ def run_multi(args):
     ms = sharded.MultiSolver(devices=list(range(ngpu))) if single else sharded.MultiSolver.for_torchrun(local)
     eff_world = ngpu if single else world
 
+    # the full-size buffers first: the small pre-flight problem then reuses them (nothing that a peer has mapped is
+    # reallocated between the two problems)
+    ms.alloc(n, paths=False)
     check = None
     if not args.skip_check:
         if single:

@@ -317,6 +317,26 @@ int multi_alloc(fw_multi *m, int n, bool want_paths) {
     if (!L.valid()) return fail(FW_ERR_INVALID, "fw_multi: no valid layout for this n / world");
     const size_t rows = (size_t)L.rows_local(), tot = rows * (size_t)L.n;
     int rc;
+    if (m->use_ipc && m->ipc_ready) {
+        // A panel buffer that peers have mapped must not be freed under them: if this layout needs bigger buffers
+        // (the same decision on every rank: the ranks share their allocation history), every rank first closes
+        // its mappings and the ranks meet before anybody reallocates.
+        Shard &s = m->sh[0];
+        bool grow = false;
+        for (int b = 0; b < 2 * L.G; ++b) grow |= s.Rw[b].cap < (size_t)FW_B * L.n;
+        if (grow) {
+            CU(cudaSetDevice(s.device));
+            CU(cudaStreamSynchronize(s.sA));
+            CU(cudaStreamSynchronize(s.sB));
+            for (auto &pr : s.peers) {
+                for (void *&q : pr.Rw) if (q) { cudaIpcCloseMemHandle(q); q = nullptr; }
+                if (pr.flags) { cudaIpcCloseMemHandle(pr.flags); pr.flags = nullptr; }
+            }
+            m->ipc_ready = false;
+            NC(g_nccl.AllReduce(s.ctx->d_flag, s.ctx->d_flag, 1, ncclInt32, ncclMax, s.comm, s.sA));   // rendezvous
+            CU(cudaStreamSynchronize(s.sA));
+        }
+    }
     for (auto &s : m->sh) {
         CU(cudaSetDevice(s.device));
         if ((rc = s.rate.ensure(tot)) != FW_OK || (rc = s.next.ensure(tot)) != FW_OK) return rc;
