@@ -145,23 +145,22 @@ __global__ void fw_spin_wait_kernel(const int *flag, int v) {
 }
 
 typedef CUresult (*StreamWaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
-StreamWaitValue32Fn g_wait_value32 = nullptr;
-bool g_wait_value32_probed = false;
+std::atomic<StreamWaitValue32Fn> g_wait_value32{nullptr};
+std::once_flag g_wait_value32_once;
 
 int stream_wait_geq(cudaStream_t st, const int *flag, int v) {
-    if (!g_wait_value32_probed) {
+    std::call_once(g_wait_value32_once, [] {
         void *fn = nullptr;
         cudaDriverEntryPointQueryResult qr;
         if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
             qr == cudaDriverEntryPointSuccess && !getenv("FW_MULTI_SPINWAIT"))
-            g_wait_value32 = reinterpret_cast<StreamWaitValue32Fn>(fn);
+            g_wait_value32.store(reinterpret_cast<StreamWaitValue32Fn>(fn));
         cudaGetLastError();
-        g_wait_value32_probed = true;
-    }
-    if (g_wait_value32) {
-        CUresult r = g_wait_value32((CUstream)st, (CUdeviceptr)(uintptr_t)flag, (cuuint32_t)v, CU_STREAM_WAIT_VALUE_GEQ);
+    });
+    if (StreamWaitValue32Fn wait = g_wait_value32.load()) {
+        CUresult r = wait((CUstream)st, (CUdeviceptr)(uintptr_t)flag, (cuuint32_t)v, CU_STREAM_WAIT_VALUE_GEQ);
         if (r == CUDA_SUCCESS) return FW_OK;
-        g_wait_value32 = nullptr;       // not supported on this stream / device: poll instead
+        g_wait_value32.store(nullptr);  // not supported on this stream / device: poll instead
     }
     fw_spin_wait_kernel<<<1, 1, 0, st>>>(flag, v);
     CU(cudaGetLastError());
