@@ -208,10 +208,13 @@ int fw_state_download(fw_state *st, double *rate, int32_t *next);
  *   fw_multi_create_rank  one process per GPU (torchrun / MPI style): this process
  *                         holds shard `rank` of `world` on `device`; nccl_id = the
  *                         128 bytes fw_multi_unique_id() produced on rank 0.
- * Transport of the 128 x n row-snapshot panel: NCCL broadcast (ncclCommInitAll /
- * ncclCommInitRank; libnccl is dlopen'ed on first use) or, single process only,
- * copy-engine peer copies (FW_MULTI_TRANSPORT=nccl|p2p; default p2p when every peer
- * is reachable, else nccl).
+ * Transport of the 128 x n row-snapshot panel (measured in DESIGN.md section 6): by
+ * default the copy engines -- cudaMemcpyPeerAsync ordered by CUDA events in one
+ * process; with one process per GPU, copies into CUDA-IPC-mapped peer buffers ordered
+ * by flag words in device memory and stream memory operations (no host round trip).
+ * FW_MULTI_TRANSPORT=nccl selects ncclBroadcast instead.  libnccl is dlopen'ed on first
+ * use: one process needs it only for that transport, rank mode also to bootstrap the
+ * ranks (exchange of the IPC handles, agreement on a validation error).
  *
  * Sharding: rows in cyclic blocks of one k-block group (ownership of the pivot
  * rows rotates over the ranks; FW_MULTI_CYCLIC=0: contiguous row blocks); k-blocks
