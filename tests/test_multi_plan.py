@@ -107,3 +107,40 @@ def test_two_rank_gloo_plan_matches_oracle(tmp_path, mode, G, cbr):
         got_x[idx] = np.load(tmp_path / f"next{r}.npy")
     assert np.array_equal(got_r.view(np.uint64), ref.rate.view(np.uint64))
     assert np.array_equal(got_x, ref.next)
+
+
+def test_global_rows_matches_the_plan_layout():
+    """sharded.global_rows (what bench.py uses to compare a shard with the oracle) is the layout of fw_plan.hpp."""
+    from floydwarshall_b200 import sharded
+    for world, rows, cbr in ((2, 32, 16), (4, 64, 16), (8, 1024, 1024), (3, 48, 8)):
+        lay = NP.Layout(rows * world, world, 8, 1, cbr)
+        for rank in range(world):
+            info = _lib.ShardInfo(rank=rank, world=world, rows=rows, cyclic_rows=cbr)
+            assert np.array_equal(sharded.global_rows(info), lay.local_rows_of(rank))
+    # every global row belongs to exactly one (rank, local row)
+    lay = NP.Layout(96, 3, 8, 2, 16)
+    allrows = np.concatenate([lay.local_rows_of(r) for r in range(3)])
+    assert sorted(allrows.tolist()) == list(range(96))
+
+
+def test_plan_random_layouts_match_oracle():
+    """Random layouts (ranks, k-blocks per group, cyclic block size in groups, number of rounds) with a tiny k-block."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=20, deadline=None)
+    @given(world=st.integers(1, 5), G=st.sampled_from([1, 2, 4]), groups_per_block=st.integers(1, 2),
+           rounds=st.integers(1, 2), seed=st.integers(0, 1000), mode=st.sampled_from(["consistent", "arbitrage", "ones"]))
+    def run(world, G, groups_per_block, rounds, seed, mode):
+        B = 4
+        cbr = G * B * groups_per_block
+        n = cbr * world * rounds
+        if n > 192:
+            return
+        C = 4
+        rate, nxt = graphs.exchange_graph(n // C, C, seed=seed, density=0.8, mode=mode)
+        ref = O.solve_dense(rate, nxt)
+        got_r, got_x = NP.run_virtual(NP.Layout(n, world, B, G, cbr), rate, nxt)
+        assert np.array_equal(got_r.view(np.uint64), ref.rate.view(np.uint64))
+        assert np.array_equal(got_x, ref.next)
+
+    run()
