@@ -233,6 +233,9 @@ int fw_multi_create(int32_t ndev, const int32_t *devices, fw_multi **out);
 int fw_multi_unique_id(void *id128);
 int fw_multi_create_rank(int32_t device, int32_t rank, int32_t world, const void *nccl_id128,
                          fw_multi **out);
+/* Rank mode: the objects of all ranks are created, used and destroyed together (every call that touches the
+ * matrix is collective, like the solve itself); keep a rank's process alive until every rank has destroyed its
+ * object, because peers hold CUDA-IPC mappings of its panel buffers until then. */
 void fw_multi_destroy(fw_multi *m);
 const char *fw_multi_last_error(fw_multi *m);
 int fw_multi_sync(fw_multi *m, int32_t n, const int32_t *ccy, int32_t n_edges, const int32_t *src,
