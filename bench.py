@@ -15,6 +15,9 @@ exchange/currency graph BASELINE.json's metric is quoted on:
 `roofline` the dominant kernel (fw_bulk_kernel) against the measured FP64 peak
 `cpu_baseline` the CPU oracle (C restatement of the reference loop, OpenMP) on a
           bounded sample of the same workload
+`configs` (N=1) / `config.check` (N>1): untimed comparisons of the CUDA results with the
+          oracle, computed in the same run.  The oracle is only ever the checker or the CPU
+          baseline here; nothing that is timed as "ours" calls it.
 
 `--impl reference` times the reference algorithm's CPU restatement (oracle/; the
 Haskell reference itself cannot be built: no ghc/cabal in the image) on the
@@ -260,7 +263,7 @@ def side_configs(ctx, dev, peak_tflops):
     (CUDA events, best of 5) and bit-exact parity against the CPU oracle, computed in this run."""
     import torch
     from floydwarshall_b200 import dense, graphs
-    from oracle import fw_oracle as O
+    from oracle import fw_oracle as O        # CHECKER only: the timed calls above it never touch the oracle
     out = {}
 
     def bits_equal(t, ref):
@@ -526,7 +529,7 @@ def preflight_check(ms, rank, world, dev):
     import torch
     import torch.distributed as dist
     from floydwarshall_b200 import graphs
-    from oracle import fw_oracle as O
+    from oracle import fw_oracle as O        # CHECKER only: untimed pre-flight comparison
     n = max(4096, 1024 * world)
     os.environ["FW_MULTI_GROUP"] = "8"
     try:
