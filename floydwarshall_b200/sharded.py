@@ -36,7 +36,7 @@ class MultiSolver:
             self._h = _handle
             return
         if devices is None:
-            ndev = ndev or self.L.fw_device_count()
+            ndev = ndev or max(1, self.L.fw_device_count())   # no device: let the library say so (FW_ERR_CUDA, no fallback)
             arr = None
         else:
             ndev = len(devices)
